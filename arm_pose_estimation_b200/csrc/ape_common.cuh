@@ -1,0 +1,102 @@
+// Shared host/device helpers of the B200 arm-pose kernels: error plumbing, quaternion algebra,
+// Philox4x32-10.  Everything marked APE_HD also compiles for the host so tests/test_host_math.py can
+// exercise the exact same source on the CPU box (see csrc/host_check.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/ape_b200.h"
+
+#define APE_HD __host__ __device__ __forceinline__
+
+namespace ape {
+
+// ---- error plumbing -------------------------------------------------------------------------------
+extern thread_local cudaError_t g_last_err;
+inline int cuda_fail(cudaError_t e) { g_last_err = e; return APE_ERR_CUDA; }
+#define APE_CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return ape::cuda_fail(_e); } while (0)
+
+inline int check_launch() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? APE_OK : cuda_fail(e);
+}
+
+// ---- quaternion algebra, [w,x,y,z], templated on the float type -----------------------------------
+template <typename F> struct Quat { F w, x, y, z; };
+template <typename F> struct Vec3 { F x, y, z; };
+
+// Hamilton product; component formulas of transformations.py:141-144
+template <typename F> APE_HD Quat<F> qmul(const Quat<F>& a, const Quat<F>& b) {
+    return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z,
+            a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+            a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
+            a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
+}
+template <typename F> APE_HD Quat<F> qconj(const Quat<F>& q) { return {q.w, -q.x, -q.y, -q.z}; }
+
+// q (x) [0,v] (x) conj(q) without normalising q (transformations.py:105-121)
+template <typename F> APE_HD Vec3<F> qrot(const Quat<F>& q, const Vec3<F>& v) {
+    Quat<F> p = {F(0), v.x, v.y, v.z};
+    Quat<F> r = qmul(qmul(q, p), qconj(q));
+    return {r.x, r.y, r.z};
+}
+// conjugate / squared norm (transformations.py:244-254)
+template <typename F> APE_HD Quat<F> qinv(const Quat<F>& q) {
+    F n = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+    return {q.w / n, -q.x / n, -q.y / n, -q.z / n};
+}
+// android [w,x,y,z] -> global axis swap [-w,x,z,y] (transformations.py:225-229)
+template <typename F> APE_HD Quat<F> android_swap(const Quat<F>& q) { return {-q.w, q.x, q.z, q.y}; }
+
+// ---- Philox4x32-10 (Salmon et al. 2011), the counter-based generator of APE_MASK_PHILOX ------------
+struct Philox4 { uint32_t v[4]; };
+
+APE_HD void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * (uint64_t)b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+}
+
+APE_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(M0, c0, hi0, lo0);
+        mulhilo32(M1, c2, hi1, lo1);
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    return {{c0, c1, c2, c3}};
+}
+
+// Dropout keep-bits of 8 consecutive hidden units [8*group, 8*group+8) of one (stream, frame, sample, gap, t).
+// Counter = (stream id, absolute frame, sample | gap<<20 | t<<24, unit group); key = 64-bit seed.
+// Each 32-bit output word yields two 16-bit lanes (low half first); unit j is kept iff lane_j < keep_thr16,
+// keep_thr16 = round((1-p) * 65536).  Independent of tiling, launch shape and GPU count by construction.
+APE_HD uint32_t philox_keep8(uint64_t seed, uint32_t stream, uint32_t frame, uint32_t sample, uint32_t gap,
+                             uint32_t t, uint32_t group, uint32_t keep_thr16) {
+    Philox4 r = philox4x32_10(stream, frame, (sample & 0xFFFFFu) | ((gap & 0xFu) << 20) | ((t & 0xFFu) << 24), group,
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        bits |= ((r.v[i] & 0xFFFFu) < keep_thr16 ? 1u : 0u) << (2 * i);
+        bits |= ((r.v[i] >> 16) < keep_thr16 ? 1u : 0u) << (2 * i + 1);
+    }
+    return bits;
+}
+
+APE_HD uint32_t keep_threshold16(float p) {
+    float k = (1.0f - p) * 65536.0f + 0.5f;
+    return k >= 65536.0f ? 65536u : (k <= 0.0f ? 0u : (uint32_t)k);
+}
+
+}  // namespace ape

@@ -1,0 +1,92 @@
+// Stage 3 math: 6D rotation -> quaternion, forward kinematics through shoulder -> elbow -> hand.
+// Host/device, templated on the float type (float on the GPU; double in host checks).
+#pragma once
+#include "ape_common.cuh"
+
+namespace ape {
+
+// Gram-Schmidt of a1 = (c0,c2,c4), a2 = (c1,c3,c5) (transformations.py:616-626), then rotation matrix ->
+// quaternion.  The reference takes the dominant eigenvector of transforms3d's 4x4 K matrix (:521-545);
+// for the orthonormal matrix produced here that equals the closed-form conversion, evaluated with the
+// best-conditioned of the four branches (largest of 4w^2,4x^2,4y^2,4z^2), then w >= 0 (:543-544).
+// `bad` is set when a column norm is zero / non-finite (the reference raises LinAlgError there).
+template <typename F> APE_HD Quat<F> six_to_quat(const F* c, bool& bad) {
+    const F a1x = c[0], a1y = c[2], a1z = c[4], a2x = c[1], a2y = c[3], a2z = c[5];
+    const F n1 = sqrt(a1x * a1x + a1y * a1y + a1z * a1z);
+    const F b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
+    const F d = b1x * a2x + b1y * a2y + b1z * a2z;
+    const F ux = a2x - d * b1x, uy = a2y - d * b1y, uz = a2z - d * b1z;
+    const F n2 = sqrt(ux * ux + uy * uy + uz * uz);
+    const F b2x = ux / n2, b2y = uy / n2, b2z = uz / n2;
+    const F b3x = b1y * b2z - b1z * b2y, b3y = b1z * b2x - b1x * b2z, b3z = b1x * b2y - b1y * b2x;
+    if (!(n1 > F(0)) || !(n2 > F(0)) || !(n1 < F(1e30)) || !(n2 < F(1e30))) bad = true;
+    // R = [b1 b2 b3] as columns: r_ij = row i, column j
+    const F r00 = b1x, r01 = b2x, r02 = b3x, r10 = b1y, r11 = b2y, r12 = b3y, r20 = b1z, r21 = b2z, r22 = b3z;
+    const F fw = F(1) + r00 + r11 + r22, fx = F(1) + r00 - r11 - r22;
+    const F fy = F(1) - r00 + r11 - r22, fz = F(1) - r00 - r11 + r22;
+    Quat<F> q;
+    if (fw >= fx && fw >= fy && fw >= fz) {
+        const F s = F(0.5) / sqrt(fw);
+        q = {fw * s, (r21 - r12) * s, (r02 - r20) * s, (r10 - r01) * s};
+    } else if (fx >= fy && fx >= fz) {
+        const F s = F(0.5) / sqrt(fx);
+        q = {(r21 - r12) * s, fx * s, (r01 + r10) * s, (r02 + r20) * s};
+    } else if (fy >= fz) {
+        const F s = F(0.5) / sqrt(fy);
+        q = {(r02 - r20) * s, (r01 + r10) * s, fy * s, (r12 + r21) * s};
+    } else {
+        const F s = F(0.5) / sqrt(fz);
+        q = {(r10 - r01) * s, (r02 + r20) * s, (r12 + r21) * s, fz * s};
+    }
+    const F inv = F(1) / sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);   // eigh returns a unit vector
+    const F sg = q.w < F(0) ? -inv : inv;
+    return {q.w * sg, q.x * sg, q.y * sg, q.z * sg};
+}
+
+// yaw-only quaternion from (sin, cos): euler_to_quat([0, atan2(s, c), 0]) (transformations.py:177-179)
+template <typename F> APE_HD Quat<F> hips_quat(F s, F c) {
+    const F y = atan2(s, c);
+    return {cos(y * F(0.5)), F(0), sin(y * F(0.5)), F(0)};
+}
+
+template <typename F> struct Body { Vec3<F> larm_vec, uarm_vec, uarm_orig; };
+
+template <typename F> struct RowPose {
+    Quat<F> larm, uarm, hips;
+    Vec3<F> hand, elbow, shoulder;
+};
+
+template <typename F> APE_HD Vec3<F> vadd(const Vec3<F>& a, const Vec3<F>& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+
+// shoulder -> elbow -> hand from the three quaternions (estimate_joints.py:61-63 / :84-85, compose_msg.py:59-61 / :92-93)
+template <typename F> APE_HD void chain(int target, const Body<F>& body, RowPose<F>& r) {
+    r.shoulder = target == APE_TARGET_ORI_CAL_LARM_UARM ? body.uarm_orig : qrot(r.hips, body.uarm_orig);
+    r.elbow = vadd(qrot(r.uarm, body.uarm_vec), r.shoulder);
+    r.hand = vadd(qrot(r.larm, body.larm_vec), r.elbow);
+}
+
+// One de-normalised target row -> quaternions + joint origins (estimate_joints.py:20-92).
+template <typename F> APE_HD RowPose<F> row_pose(int target, const F* p, const Body<F>& body, bool& bad) {
+    RowPose<F> r;
+    r.hips = {F(1), F(0), F(0), F(0)};
+    if (target == APE_TARGET_ORI_POS_CAL_LARM_UARM_HIPS) {
+        r.larm = six_to_quat(p + 3, bad);
+        r.uarm = six_to_quat(p + 12, bad);
+        r.hips = hips_quat(p[18], p[19]);
+        r.hand = {p[0], p[1], p[2]};
+        r.elbow = {p[9], p[10], p[11]};
+        r.shoulder = qrot(r.hips, body.uarm_orig);
+        return r;
+    }
+    r.larm = six_to_quat(p, bad);
+    r.uarm = six_to_quat(p + 6, bad);
+    if (target == APE_TARGET_ORI_CAL_LARM_UARM_HIPS) r.hips = hips_quat(p[12], p[13]);
+    chain(target, body, r);
+    return r;
+}
+
+APE_HD int target_num_outputs(int target) {
+    return target == APE_TARGET_ORI_CAL_LARM_UARM ? 12 : (target == APE_TARGET_ORI_CAL_LARM_UARM_HIPS ? 14 : 20);
+}
+
+}  // namespace ape

@@ -1,0 +1,211 @@
+"""The batched per-frame estimation path: many streams x MC samples in one pass on one B200.
+
+``BatchedEstimator`` is what the reference's per-stream loop (``estimator.py:155-178``: ``parse_row_to_xx`` ->
+``add_xx_to_row_hist_and_make_prediction`` -> ``msg_from_pred``) becomes when B independent streams advance in
+lockstep: one H2D copy of the raw rows ``[B, nF, 28|55]``, three kernel stages on one CUDA stream
+(``ape_features`` -> ``ape_mc_lstm_*`` -> ``ape_fk_reduce``), one D2H copy of the 25-float messages (+ std, + per-sample
+hand / elbow positions).  All history the reference keeps in Python lists (``_row_hist``, ``_smooth_hist``) lives in
+device rings indexed by the absolute frame number; frames before 0 clamp to frame 0, which is the reference's
+"repeat the first row / first prediction" warm-up.  Streams are independent, so a multi-GPU job is a static split
+of the stream axis (``shard_streams``) with no collective.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from arm_pose_estimation_b200 import _native as N
+from arm_pose_estimation_b200.data_types.bone_map import body_measurements_row
+from arm_pose_estimation_b200.estimate import nn_models
+from arm_pose_estimation_b200.utility.names import NNS_TARGETS
+
+TARGET_IDS = {
+    NNS_TARGETS.ORI_CAL_LARM_UARM: N.TARGET_ORI_CAL_LARM_UARM,
+    NNS_TARGETS.ORI_CAL_LARM_UARM_HIPS: N.TARGET_ORI_CAL_LARM_UARM_HIPS,
+    NNS_TARGETS.ORI_POS_CAL_LARM_UARM_HIPS: N.TARGET_ORI_POS_CAL_LARM_UARM_HIPS,
+}
+EST_WIDTH = {N.TARGET_ORI_CAL_LARM_UARM: 14, N.TARGET_ORI_CAL_LARM_UARM_HIPS: 21, N.TARGET_ORI_POS_CAL_LARM_UARM_HIPS: 21}
+KIND_FEATURES = {N.KIND_WATCH_ONLY: 20, N.KIND_POCKET: 22, N.KIND_UARM: 38}
+LAYOUT_NCOLS = {N.LAYOUT_WATCH_ONLY: 28, N.LAYOUT_WATCH_PHONE: 55}
+
+
+def shard_streams(n_streams, world_size, rank):
+    """Static contiguous split of the stream axis: ``(first_stream, count)`` of ``rank``.
+    The first ``n_streams % world_size`` ranks take one extra stream; no stream is shared, no exchange follows."""
+    if world_size < 1 or not 0 <= rank < world_size or n_streams < 0:
+        raise ValueError(f"bad shard request: n_streams={n_streams} world_size={world_size} rank={rank}")
+    base, extra = divmod(n_streams, world_size)
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def ring_slots(n_frames_per_call, history):
+    """Slots a device ring needs so that one call of ``n_frames_per_call`` frames still finds the ``history - 1``
+    frames before its first one (``history`` = sequence_len for features, smooth for predictions)."""
+    return max(1, n_frames_per_call) + max(1, history) - 1
+
+
+@dataclass
+class EstimateBatch:
+    """Results of one ``BatchedEstimator.step``; tensors live on the estimator's device until ``.host()``."""
+    msg: torch.Tensor            # [B, nF, 25]   [larm_q, hand, larm_q, elbow, uarm_q, shoulder, hips_q] (compose_msg.py)
+    std: torch.Tensor            # [B, nF, 6]    population std of the per-row hand / elbow positions
+    samples: torch.Tensor        # [B, nF, S, 6] per-row hand xyz, elbow xyz (message tail of estimator.py:131-136) or None
+    status: torch.Tensor         # [B, nF] int32, 1 = degenerate 6D output (the reference raises LinAlgError)
+    frame0: int
+
+    def host(self):
+        f = lambda t: None if t is None else t.cpu().numpy()
+        return EstimateBatch(f(self.msg), f(self.std), f(self.samples), f(self.status), self.frame0)
+
+
+class BatchedEstimator:
+    def __init__(self, kind, layout, state, seq_len, y_targets, stats, n_streams, mc_samples,
+                 smooth=1, dropout=0.2, bonemap=None, frames_per_call=1, emit_samples=True, normalize=True,
+                 mask_mode=N.MASK_PHILOX, philox_seed=0, first_stream=0, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedEstimator needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = N.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.kind, self.layout = int(kind), int(layout)
+        self.I, self.H, self.L, self.O = nn_models.lstm_dims(state)
+        if KIND_FEATURES[self.kind] != self.I:
+            raise UserWarning(f"estimator kind {kind} produces {KIND_FEATURES[self.kind]} features, the model takes {self.I}")
+        self.T, self.smooth, self.n = max(1, int(seq_len)), max(1, int(smooth)), int(mc_samples)
+        self.S = self.smooth * self.n
+        self.p = float(dropout)
+        self.B, self.nF_max = int(n_streams), max(1, int(frames_per_call))
+        self.target = TARGET_IDS[y_targets]
+        if self.O != len(y_targets.value):
+            raise UserWarning(f"model has {self.O} outputs, target set {y_targets.name} has {len(y_targets.value)}")
+        self.mask_mode, self.philox_seed, self.first_stream = int(mask_mode), int(philox_seed), int(first_stream)
+        self.emit_samples = bool(emit_samples)
+        self.normalize = bool(normalize)
+        self.ncols = LAYOUT_NCOLS[self.layout]
+        dev, f32 = self.device, torch.float32
+        with torch.cuda.device(dev):
+            self.weights = torch.from_numpy(nn_models.pack_lstm_weights(state)).to(dev)
+            if normalize:
+                self.xx_m = torch.as_tensor(np.asarray(stats["xx_m"], dtype=np.float64)).to(dev)
+                self.xx_s = torch.as_tensor(np.asarray(stats["xx_s"], dtype=np.float64)).to(dev)
+                self.yy_m = torch.as_tensor(np.asarray(stats["yy_m"], dtype=np.float32)).to(dev)
+                self.yy_s = torch.as_tensor(np.asarray(stats["yy_s"], dtype=np.float32)).to(dev)
+            else:
+                self.xx_m = self.xx_s = self.yy_m = self.yy_s = None
+            self.body = torch.as_tensor(body_measurements_row(bonemap).astype(np.float32).ravel()).to(dev)
+            self.feat_ring = ring_slots(self.nF_max, self.T)
+            self.pred_ring = ring_slots(self.nF_max, self.smooth)
+            B, nF = self.B, self.nF_max
+            self.raw = torch.zeros((B, nF, self.ncols), dtype=f32, device=dev)
+            self.feats = torch.zeros((B, self.feat_ring, self.I), dtype=f32, device=dev)
+            self.preds = torch.zeros((B, self.pred_ring, self.n, self.O), dtype=f32, device=dev)
+            self.msg = torch.zeros((B, nF, 25), dtype=f32, device=dev)
+            self.std = torch.zeros((B, nF, 6), dtype=f32, device=dev)
+            self.samples = torch.zeros((B, nF, self.S, 6), dtype=f32, device=dev) if emit_samples else None
+            self.status = torch.zeros((B, nF), dtype=torch.int32, device=dev)
+            # sized for the largest call; a shorter call re-tiles its rows, so leave one tile of slack per buffer
+            ws_bytes = N.workspace_bytes(self.I, self.H, self.L, self.T, self.O, B * nF, self.n) + 3 * 64 * self.T * self.H * 4
+            self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            # pinned staging for the host-facing calls
+            self.raw_host = torch.zeros((B, nF, self.ncols), dtype=f32).pin_memory()
+            self.msg_host = torch.zeros((B, nF, 25), dtype=f32).pin_memory()
+            self.std_host = torch.zeros((B, nF, 6), dtype=f32).pin_memory()
+            self.samples_host = torch.zeros((B, nF, self.S, 6), dtype=f32).pin_memory() if emit_samples else None
+            self.status_host = torch.zeros((B, nF), dtype=torch.int32).pin_memory()
+        self.frame = 0
+        self.launches = 0             # kernels launched so far (bench.py reports it)
+
+    def reset(self):
+        """Forget all history, like ``Estimator.reset`` (estimator.py:88-91): the next row is frame 0 again."""
+        self.frame = 0
+
+    # ---- device path -----------------------------------------------------------------------------------
+    def step_device(self, raw, n_frames=None, masks=None, layer_ms=None):
+        """``raw``: device tensor ``[B, nF, ncols]`` float32 (nF <= frames_per_call).  Enqueues the three stages
+        on the current stream and returns an ``EstimateBatch`` of views into the estimator's device buffers."""
+        nF = int(raw.shape[1]) if n_frames is None else int(n_frames)
+        if raw.shape[0] != self.B or nF > self.nF_max or raw.shape[2] != self.ncols or not raw.is_contiguous():
+            raise UserWarning(f"raw rows must be a contiguous [B={self.B}, nF<={self.nF_max}, {self.ncols}] tensor, got {tuple(raw.shape)}")
+        if raw.dtype != torch.float32:
+            raise UserWarning("raw rows must be float32 (the wire format, messaging.py)")
+        lib, st, B = self.lib, N.current_stream_ptr(), self.B
+        N.check(lib.ape_features(N.ptr(raw), self.layout, self.kind, N.ptr(self.xx_m), N.ptr(self.xx_s),
+                                 1 if self.normalize else 0, N.ptr(self.feats), B, nF, self.frame, self.feat_ring, st),
+                "ape_features")
+        a = N.LstmArgs()
+        a.weights = self.weights.data_ptr()
+        a.I, a.H, a.L, a.T, a.O = self.I, self.H, self.L, self.T, self.O
+        a.dropout_p = self.p
+        a.x_dense, a.feat_ring_buf, a.feat_ring = None, self.feats.data_ptr(), self.feat_ring
+        a.B, a.nF, a.frame0, a.n_samples = B, nF, self.frame, self.n
+        a.mask_mode = self.mask_mode if self.L > 1 else N.MASK_NONE
+        md = None
+        if a.mask_mode == N.MASK_INJECTED:
+            if masks is None:
+                raise UserWarning("mask_mode is MASK_INJECTED: pass masks [B, nF, L-1, T, n, H] uint8")
+            md = torch.as_tensor(masks).to(device=self.device, dtype=torch.uint8).contiguous()
+            if md.numel() != B * nF * (self.L - 1) * self.T * self.n * self.H:
+                raise UserWarning("masks must be [B, nF, L-1, T, n, H]")
+            a.masks = md.data_ptr()
+        a.philox_seed, a.stream_id0 = self.philox_seed, self.first_stream
+        a.workspace = self.workspace.data_ptr()
+        a.preds, a.pred_ring, a.all_steps = self.preds.data_ptr(), self.pred_ring, 0
+        if layer_ms is not None:                     # profiling leg: float32 host array of L entries, filled on return
+            a.layer_ms = layer_ms.ctypes.data
+        N.check(lib.ape_mc_lstm_fma(a, st), "ape_mc_lstm")
+        N.check(lib.ape_fk_reduce(N.ptr(self.preds), self.pred_ring, N.ptr(self.yy_m), N.ptr(self.yy_s), N.ptr(self.body),
+                                  self.target, self.O, B, nF, self.frame, self.n, self.smooth,
+                                  N.ptr(self.msg), N.ptr(self.samples), N.ptr(self.std), None, N.ptr(self.status), st),
+                "ape_fk_reduce")
+        self.launches += 2 + self.L
+        out = EstimateBatch(self._view(self.msg, nF), self._view(self.std, nF), self._view(self.samples, nF),
+                            self._view(self.status, nF), self.frame)
+        self.frame += nF
+        return out
+
+    def _view(self, buf, nF):
+        """The kernels pack a call's E = B * nF estimates densely: view the front of a [B, nF_max, ...] buffer."""
+        if buf is None:
+            return None
+        tail = tuple(buf.shape[2:])
+        return buf.reshape(-1)[: self.B * nF * int(np.prod(tail, dtype=np.int64))].view(self.B, nF, *tail)
+
+    # ---- host-facing path: pinned H2D, the three stages, pinned D2H ------------------------------------------
+    def step(self, rows, masks=None, sync=True):
+        """``rows``: host array ``[B, nF, ncols]`` (or ``[B, ncols]`` for one frame) of float32 wire rows.
+        Returns an ``EstimateBatch`` of HOST arrays (views of pinned buffers, valid until the next call)."""
+        rows = np.asarray(rows, dtype=np.float32)
+        if rows.ndim == 2:
+            rows = rows[:, None, :]
+        nF = rows.shape[1]
+        if rows.shape[0] != self.B or nF > self.nF_max or rows.shape[2] != self.ncols:
+            raise UserWarning(f"rows must be [B={self.B}, nF<={self.nF_max}, {self.ncols}], got {rows.shape}")
+        with torch.cuda.device(self.device):
+            if nF == self.nF_max:
+                self.raw_host.numpy()[...] = rows
+                self.raw.copy_(self.raw_host, non_blocking=True)
+                raw = self.raw
+            else:                                        # short call: a contiguous [B, nF, ncols] staging view
+                raw = torch.from_numpy(np.ascontiguousarray(rows)).to(self.device)
+            out = self.step_device(raw, nF, masks)
+            host = []
+            for dev_t, host_buf in ((out.msg, self.msg_host), (out.std, self.std_host), (out.samples, self.samples_host),
+                                    (out.status, self.status_host)):
+                if dev_t is None:
+                    host.append(None)
+                    continue
+                hv = self._view(host_buf, nF)
+                hv.copy_(dev_t, non_blocking=True)
+                host.append(hv.numpy())
+            if sync:
+                torch.cuda.current_stream().synchronize()
+        return EstimateBatch(host[0], host[1], host[2], host[3], out.frame0)
+
+    @property
+    def h2d_bytes_per_frame(self):
+        return self.B * self.ncols * 4
+
+    @property
+    def d2h_bytes_per_frame(self):
+        return self.B * ((25 + 6) * 4 + 4 + (self.S * 6 * 4 if self.emit_samples else 0))

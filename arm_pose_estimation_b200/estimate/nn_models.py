@@ -1,0 +1,222 @@
+"""The MC-dropout LSTM regressor behind the reference's model API (``estimate/nn_models.py:160-207``, ``:373-424``).
+
+``DropoutLSTM`` keeps the constructor, attributes, ``forward(x, hs=None)``, ``monte_carlo_predictions(n_samples, x,
+hs=None)``, ``load_state_dict`` / ``state_dict`` / ``eval`` surface of the reference module, but the arithmetic is
+the CUDA path of ``csrc/`` reached through the C ABI (``include/ape_b200.h``): there is no torch.nn module
+underneath and no CPU fallback.  Differences a caller can see:
+
+* dropout masks come from counter-based Philox keyed by ``(seed; stream, call index, sample, gap, t, unit)``
+  instead of torch's CPU generator; ``monte_carlo_predictions(..., masks=...)`` injects explicit masks
+  (time-major ``(L-1, T, n, H)``, the order torch draws them - SURVEY.md §3.2) for bit-comparable runs;
+* layer 0 is evaluated once per input row, layers >= 1 once per MC sample (same results, fewer flops).
+"""
+import hashlib
+import json
+import logging
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from arm_pose_estimation_b200 import _native as N
+from arm_pose_estimation_b200 import config
+
+
+def lstm_dims(state):
+    """(I, H, L, O) from the reference's state-dict key shapes."""
+    H4, I = state["lstm.weight_ih_l0"].shape
+    L = sum(1 for k in state if k.startswith("lstm.weight_ih_l"))
+    return int(I), int(H4) // 4, int(L), int(state["output_layer.weight"].shape[0])
+
+
+def pack_lstm_weights(state):
+    """Reference state dict -> the flat float32 blob of ``csrc/ape_lstm_pack.h``.
+
+    Per layer a K-major matrix ``Wp[k][4*u + g]`` (input rows zero-padded to a multiple of 16, then the
+    recurrent rows) followed by the summed bias; then ``output_layer.weight`` (O, H) and ``.bias`` (O)."""
+    st = {k: np.asarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
+          for k, v in state.items()}
+    I, H, L, O = lstm_dims(st)
+    parts = []
+    for l in range(L):
+        w_ih, w_hh = st[f"lstm.weight_ih_l{l}"], st[f"lstm.weight_hh_l{l}"]
+        kin = w_ih.shape[1]
+        kin_pad = -(-kin // N.KSLICE) * N.KSLICE if l == 0 else H
+        wp = np.zeros((kin_pad + H, 4 * H), np.float32)
+        wp[:kin] = w_ih.reshape(4, H, kin).transpose(2, 1, 0).reshape(kin, 4 * H)
+        wp[kin_pad:] = w_hh.reshape(4, H, H).transpose(2, 1, 0).reshape(H, 4 * H)
+        bias = (st[f"lstm.bias_ih_l{l}"] + st[f"lstm.bias_hh_l{l}"]).reshape(4, H).T.reshape(4 * H)
+        parts += [wp.ravel(), bias]
+    parts += [st["output_layer.weight"].ravel(), st["output_layer.bias"].ravel()]
+    return np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+
+
+def packed_floats(I, H, L, O):
+    """Python mirror of ``ape_pack_total_floats`` (checked against the library in tests/test_cabi.py)."""
+    kin0 = -(-I // N.KSLICE) * N.KSLICE
+    return (kin0 + H) * 4 * H + 4 * H + (L - 1) * (2 * H * 4 * H + 4 * H) + O * H + O
+
+
+class _LstmMode:
+    """Stand-in for the ``model.lstm`` sub-module: only its train / eval switch matters (nn_models.py:204)."""
+
+    def __init__(self):
+        self.training = False
+
+    def train(self, mode=True):
+        self.training = bool(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("arm_pose_estimation_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+class DropoutLSTM:
+    def __init__(self, input_size, hidden_layer_size, hidden_layer_count, output_size, dropout=0.2,
+                 philox_seed=None, precision="fp32"):
+        self.output_size = int(output_size)
+        self.input_size = int(input_size)
+        self.hidden_layer_size = int(hidden_layer_size)
+        self.hidden_layer_count = int(hidden_layer_count)
+        self.dropout = float(dropout)
+        self.precision = precision
+        self.lstm = _LstmMode()
+        self.philox_seed = int(torch.initial_seed() if philox_seed is None else philox_seed) & (2 ** 64 - 1)
+        self._calls = 0                      # Philox "frame" counter: fresh masks on every call
+        self._state = None
+        self._blob = None                    # device copy of the packed weights (built lazily)
+        self._ws = None
+
+    # ---- torch.nn.Module-like surface ---------------------------------------------------------------
+    def load_state_dict(self, state):
+        I, H, L, O = lstm_dims(state)
+        if (I, H, L, O) != (self.input_size, self.hidden_layer_size, self.hidden_layer_count, self.output_size):
+            raise RuntimeError(f"state dict is for (I,H,L,O)={(I, H, L, O)}, model is "
+                               f"{(self.input_size, self.hidden_layer_size, self.hidden_layer_count, self.output_size)}")
+        self._state = {k: torch.as_tensor(np.asarray(v.detach().cpu() if isinstance(v, torch.Tensor) else v,
+                                                     dtype=np.float32)) for k, v in state.items()}
+        self._blob = None
+        return self
+
+    def state_dict(self):
+        return dict(self._state)
+
+    def eval(self):
+        self.lstm.eval()
+        return self
+
+    def train(self, mode=True):
+        self.lstm.train(mode)
+        return self
+
+    def packed_weights(self):
+        """Device tensor holding the packed weight blob."""
+        _require_cuda()
+        if self._state is None:
+            raise UserWarning("model has no weights: call load_state_dict first")
+        if self._blob is None:
+            self._blob = torch.from_numpy(pack_lstm_weights(self._state)).cuda()
+        return self._blob
+
+    def _workspace(self, T, E, n):
+        need = N.workspace_bytes(self.input_size, self.hidden_layer_size, self.hidden_layer_count, T,
+                                 self.output_size, E, n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+        return self._ws
+
+    def _run(self, x, n_samples, mask_mode, masks=None):
+        _require_cuda()
+        if x.dim() != 3 or x.shape[2] != self.input_size:
+            raise UserWarning(f"expected x of shape [batch, sequence, {self.input_size}], got {tuple(x.shape)}")
+        host_in = not x.is_cuda
+        xd = x.detach().to(device="cuda", dtype=torch.float32).contiguous()
+        E, T, _ = xd.shape
+        L, H, O = self.hidden_layer_count, self.hidden_layer_size, self.output_size
+        n_kernel = 1 if L == 1 else n_samples            # no dropout in a single-layer model: samples are identical
+        preds = torch.empty((E, n_kernel, T, O), dtype=torch.float32, device="cuda")
+        a = N.LstmArgs()
+        a.weights = self.packed_weights().data_ptr()
+        a.I, a.H, a.L, a.T, a.O = self.input_size, H, L, T, O
+        a.dropout_p = self.dropout
+        a.x_dense, a.feat_ring_buf, a.feat_ring = xd.data_ptr(), None, 0
+        a.B, a.nF, a.frame0 = E, 1, self._calls & 0x7FFFFFFF
+        a.n_samples = n_kernel
+        a.mask_mode = mask_mode
+        md = None
+        if mask_mode == N.MASK_INJECTED and L > 1:
+            md = torch.as_tensor(np.asarray(masks) if not isinstance(masks, torch.Tensor) else masks)
+            md = md.to(device="cuda", dtype=torch.uint8).contiguous()
+            if md.numel() != E * (L - 1) * T * n_kernel * H:
+                raise UserWarning(f"masks must hold E*(L-1)*T*n*H = {E * (L - 1) * T * n_kernel * H} entries, got {md.numel()}")
+            a.masks = md.data_ptr()
+        a.philox_seed, a.stream_id0 = self.philox_seed, 0
+        ws = self._workspace(T, E, n_kernel)
+        a.workspace = ws.data_ptr()
+        a.preds, a.pred_ring, a.all_steps = preds.data_ptr(), 1, 1
+        N.check(N.load().ape_mc_lstm_fma(a, N.current_stream_ptr()), "ape_mc_lstm_fma")
+        self._calls += 1
+        out = preds.reshape(E * n_kernel, T, O)
+        if n_kernel != n_samples:
+            out = out.repeat_interleave(n_samples, dim=0)
+        return out.cpu() if host_in else out
+
+    def forward(self, x, hs=None):
+        """``x [batch, sequence, input] -> [batch, sequence, output]`` (nn_models.py:180-189)."""
+        if hs is not None:
+            raise UserWarning("a caller-supplied initial (h_0, c_0) is not supported: the estimators always start from zeros")
+        return self._run(x, 1, N.MASK_PHILOX if self.lstm.training else N.MASK_NONE)
+
+    __call__ = forward
+
+    def monte_carlo_predictions(self, n_samples, x, hs=None, masks=None):
+        """``x [1, sequence, input] -> [n_samples, sequence, output]`` with dropout active (nn_models.py:191-207)."""
+        if x.shape[0] > 1:
+            raise UserWarning("MC predictions only for batch size 1")
+        if hs is not None:
+            raise UserWarning("a caller-supplied initial (h_0, c_0) is not supported: the estimators always start from zeros")
+        self.lstm.train()
+        if masks is not None:
+            return self._run(x, n_samples, N.MASK_INJECTED, masks)
+        return self._run(x, n_samples, N.MASK_PHILOX)
+
+
+def load_deployed_model_from_hash(hash_str: str):
+    """``(model, params)`` from ``<deploy>/nn/<hash>/{results.json, checkpoint.pt}`` (nn_models.py:373-415);
+    the checkpoint is the ``(model_state, optimizer_state)`` tuple the reference saves."""
+    save_path = Path(config.PATHS["deploy"]) / "nn" / hash_str
+    json_path, chkpt_path = save_path / "results.json", save_path / "checkpoint.pt"
+    if not json_path.exists():
+        raise UserWarning(f"no json found {json_path}")
+    if not chkpt_path.exists():
+        raise UserWarning(f"no checkpoint found {chkpt_path}")
+    with open(json_path, "r") as f:
+        params = json.load(f)
+    if params["model"] == "DropoutLSTM":
+        params["model"] = DropoutLSTM
+    else:
+        raise UserWarning(f"{params['model']} not handled")
+    nn_model = params["model"](
+        input_size=len(params["x_inputs_v"]),
+        hidden_layer_size=params["hidden_layer_size"],
+        hidden_layer_count=params["hidden_layer_count"],
+        output_size=len(params["y_targets_v"]),
+        dropout=params["dropout"],
+    )
+    model_state, _ = torch.load(chkpt_path, map_location="cpu")
+    nn_model.load_state_dict(model_state)
+    nn_model.eval()
+    logging.info("loaded model in eval mode from {}".format(save_path))
+    return nn_model, params
+
+
+def get_nn_name(params):
+    """SHA-1 of the parameter dictionary's ``str`` (nn_models.py:418-424)."""
+    sha1 = hashlib.sha1()
+    sha1.update(str(params).encode("utf-8"))
+    return str(sha1.hexdigest())

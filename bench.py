@@ -1,0 +1,332 @@
+"""Benchmark of the per-frame arm-pose estimation hot path (BASELINE.json's metric: MC-sampled arm-pose
+estimates/sec at 1/2/4/8 B200 vs the reference CPU path, and % of roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (configs[2] of BASELINE.json, the largest single-GPU configuration and the one the throughput metric
+is quoted on): watch+phone upper-arm estimator (I38 H128 L3 T6 O12) with quaternion FK, 1024 concurrent streams
+x 100 MC samples PER GPU (weak scaling: streams are sharded, no collective), synthetic IMU rows, seeded
+random-init weights.  One step = one frame of every stream = 1024 estimates per GPU.
+
+  value      estimates/s, whole job, inputs resident in HBM, CUDA events, max over ranks
+  e2e        the same metric through BatchedEstimator.step() with HOST rows: pinned H2D of the raw rows and D2H
+             of messages + std + per-sample positions inside the timed region, every step
+  roofline   the dominant kernel (an LSTM layer >= 1 launch): algorithmic flops / its device time (events
+             recorded by the library around each layer launch), against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the oracle's restatement of the reference CPU path (torch.nn.LSTM on the CPU +
+             numpy FK, exactly the arithmetic the reference executes) timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (kind, streams per GPU, MC samples, smooth)
+    "uarm_1024x100": (2, 1024, 100, 1),
+    "pocket_1x100": (1, 1, 100, 1),
+    "watch_only_1024x100": (0, 1024, 100, 1),
+}
+METRIC, UNIT = "mc_sampled_arm_pose_estimates_per_sec", "estimates/s"
+
+
+def algorithmic_flops_per_estimate(I, H, L, T, O, n):
+    """F(n) of SURVEY.md §8d: layer 0 once per estimate, layers >= 1 per MC sample, output layer on the last step."""
+    return T * 2 * 4 * H * (I + H) + n * (L - 1) * T * 2 * 4 * H * (2 * H) + n * 2 * H * O
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md's clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = max(smax, float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- the reference CPU path (oracle port), used by cpu_baseline and --impl reference --------------------------------
+_W = {}
+
+
+def _cpu_worker_init(kind, n, smooth, threads):
+    """Per-process set-up: one single-stream oracle estimator (torch CPU LSTM + numpy FK) and its synthetic rows."""
+    import torch
+    torch.set_num_threads(threads)
+    from arm_pose_estimation_b200 import synthetic as syn
+    from oracle import estimator as OE
+    spec = syn.kind_spec(kind)
+    state = syn.synth_state_dict(spec["I"], spec["H"], spec["L"], spec["O"], 1234 + kind)
+    _W["orc"] = OE.OracleEstimator(syn.KIND_NAMES[kind], spec["lookup"], state, spec["stats"], spec["y_targets"].name,
+                                   spec["T"], smooth, n, None, spec["p"], mask_source="torch")
+    _W["rows"] = syn.synth_rows(kind, 1, 256, config_id=3, first_stream=os.getpid() % 1000)[0]
+    _W["pos"] = 0
+    for r in _W["rows"][:3]:
+        _W["orc"].step(r)                                     # warm-up frames
+
+
+def _cpu_worker_frames(n_frames):
+    orc, rows = _W["orc"], _W["rows"]
+    t0 = time.perf_counter()
+    for _ in range(n_frames):
+        orc.step(rows[_W["pos"] % len(rows)])                 # the three calls of estimator.py:174-176
+        _W["pos"] += 1
+    return n_frames, time.perf_counter() - t0
+
+
+class CpuReference:
+    """The reference CPU path on `workers` independent single-stream processes (the reference is single-stream by
+    construction, nn_models.py:201-202): `rate(frames)` = summed estimates/s over one bounded sample."""
+
+    def __init__(self, kind, n, smooth, workers, threads_per_worker=1):
+        import multiprocessing as mp
+        self.workers = workers
+        self.pool = mp.get_context("spawn").Pool(workers, initializer=_cpu_worker_init,
+                                                 initargs=(kind, n, smooth, threads_per_worker))
+
+    def rate(self, frames_per_worker):
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker_frames, [frames_per_worker] * self.workers, chunksize=1)
+        wall = time.perf_counter() - t0
+        return sum(f for f, _ in res) / max(dt for _, dt in res), wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    kind, B, n, smooth = WORKLOADS[args.workload]
+    workers = max(1, min(os.cpu_count() or 1, 64))
+    ref = CpuReference(kind, n, smooth, workers)
+    for _ in range(args.warmup):
+        ref.rate(2)
+    rates, t_all = [], time.perf_counter()
+    for _ in range(args.steps):
+        rates.append(ref.rate(args.ref_frames)[0])
+    wall = time.perf_counter() - t_all
+    ref.close()
+    value = float(np.mean(rates))
+    sample = (f"{workers} single-stream worker processes (1 thread each) x {args.ref_frames} frames per step of the {args.workload} "
+              f"workload (n={n} MC samples, smooth={smooth}); torch.nn.LSTM on CPU + numpy FK (oracle port of the reference path)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "streams_per_gpu": B, "mc_samples": n, "smooth": smooth},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm -----------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from arm_pose_estimation_b200 import _native as N, synthetic as syn
+    from arm_pose_estimation_b200.estimate.batched import BatchedEstimator, shard_streams
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    kind, B, n, smooth = WORKLOADS[args.workload]
+    spec = syn.kind_spec(kind)
+    I, H, L, T, O = (spec[k] for k in "IHLTO")
+    state = syn.synth_state_dict(I, H, L, O, 1234 + kind)
+    first, count = shard_streams(B * world, world, rank)      # weak scaling: B streams per GPU, global stream ids
+    be = BatchedEstimator(kind=kind, layout=spec["layout"], state=state, seq_len=T, y_targets=spec["y_targets"],
+                          stats=spec["stats"], n_streams=count, mc_samples=n, smooth=smooth, dropout=spec["p"],
+                          frames_per_call=1, mask_mode=N.MASK_PHILOX, philox_seed=2026, first_stream=first,
+                          emit_samples=True)
+    K, W = args.steps, args.warmup
+    # synthetic rows: 64 distinct seeded streams tiled over the shard (generation cost only), K+W frames
+    base = syn.synth_rows(kind, min(64, count), K + W, config_id=3, first_stream=first)
+    rows = np.ascontiguousarray(np.tile(base, (-(-count // base.shape[0]), 1, 1))[:count])
+    rows_dev = torch.from_numpy(rows).cuda()
+    frames_dev = [rows_dev[:, f:f + 1].contiguous() for f in range(K + W)]
+    frames_host = [np.ascontiguousarray(rows[:, f:f + 1]) for f in range(K + W)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value") ----
+    be.reset()
+    for f in range(W):
+        be.step_device(frames_dev[f])
+    barrier()
+    launches0 = be.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        for f in range(W, W + K):
+            be.step_device(frames_dev[f])
+        ev1.record()
+        barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = be.launches - launches0
+    clocks = clk.summary()
+
+    # ---- end to end through the public host-facing call ----
+    be.reset()
+    for f in range(W):
+        be.step(frames_host[f])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    checksum = 0.0
+    for f in range(W, W + K):
+        out = be.step(frames_host[f])                         # pinned H2D -> 3 stages -> pinned D2H, synchronised
+        checksum += float(out.msg[0, 0, 4])
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- roofline leg: per-layer device time of the LSTM stage (events recorded by the library) ----
+    layer_ms = np.zeros(L, np.float32)
+    acc = np.zeros(L, np.float64)
+    reps = max(3, min(K, 10))
+    for f in range(reps):
+        be.step_device(frames_dev[W + f % K], layer_ms=layer_ms)
+        acc += layer_ms
+    torch.cuda.synchronize()
+    acc /= reps
+    peaks, peak_src = measured_peaks()
+    rows_mc = count * n
+    dom_flops = rows_mc * T * 2 * 4 * H * (2 * H)             # one layer >= 1 launch, algorithmic
+    dom_ms = float(np.mean(acc[1:-1])) if L > 2 else float(acc[-1])   # a middle layer (no output GEMM); L=2: the last
+    fp32_peak_tflops = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
+    achieved = dom_flops / (dom_ms * 1e-3) / 1e12
+    total_est = count * K * world
+
+    line = {
+        "metric": METRIC, "value": total_est / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "baseline_config": "watch+phone upper-arm estimator with quaternion FK, 1024 concurrent streams x 100 MC samples on 1 B200",
+                   "model": {"I": I, "H": H, "L": L, "T": T, "O": O, "dropout": spec["p"]}, "streams_per_gpu": count,
+                   "mc_samples": n, "smooth": smooth, "frames_per_step": 1, "estimates_per_step_per_gpu": count,
+                   "lstm_variant": "fp32_ffma", "rng": "philox4x32-10",
+                   "l2": f"per-step working set (inter-layer sequences {rows_mc * T * H * 4 / 1e6:.0f} MB) exceeds the 126 MB L2"},
+        "e2e": {"value": total_est / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": be.h2d_bytes_per_frame,
+                "d2h_bytes_per_step": be.d2h_bytes_per_frame, "ms_per_step": e2e_ms / K},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "fp32_ffma", "kernel": "lstm_layer_fma_kernel (one layer >= 1 launch)", "achieved": achieved,
+                     "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
+                     "peak_source": f"148 SM x 128 FFMA/clk x 2 x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz (nominal fp32 FMA peak at max SM clock; "
+                                    f"MEASURED_PEAKS.json [{peak_src}] has no fp32 figure)",
+                     "frac_of_bf16_tensor_peak": achieved / peaks["bf16_tflops"],
+                     "flops_per_launch": dom_flops, "ms_per_launch": dom_ms, "layer_ms": [float(v) for v in acc], "traffic": None},
+        "checksum": checksum,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        workers = max(1, min(os.cpu_count() or 1, 64))
+        ref = CpuReference(kind, n, smooth, workers)
+        ref.rate(2)
+        rate, wall = ref.rate(args.cpu_frames)
+        ref.close()
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": workers, "kind": "port",
+                                "sample": f"{workers} single-stream worker processes (1 thread each) x {args.cpu_frames} frames of the "
+                                          f"{args.workload} workload (n={n}); torch.nn.LSTM on CPU + numpy FK; {wall:.1f} s of CPU work"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="uarm_1024x100", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-frames", type=int, default=400, help="frames per worker of the bounded cpu_baseline sample")
+    ap.add_argument("--ref-frames", type=int, default=100, help="--impl reference: frames per worker per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if world != args.gpus and world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

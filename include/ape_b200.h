@@ -1,0 +1,159 @@
+/*
+ * ape_b200.h - C ABI of the B200-native per-frame arm-pose estimation path.
+ *
+ * The reference (wear_mocap_ape 1.2.3) has no FFI: its boundary is the Python class API
+ * (SURVEY.md §8b).  This header is the C-ABI layer north_star prescribes underneath that API.
+ * Every entry point takes raw DEVICE pointers + sizes + a cudaStream_t (passed as void*), allocates
+ * nothing, keeps no global state, and returns an int status (APE_OK or an APE_ERR_* code; the Python
+ * wrappers raise UserWarning on non-zero, the way the reference signals errors, nn_models.py:202).
+ * All kernels are enqueued on `stream` and return without synchronising.
+ *
+ * Units.  One ESTIMATE = one frame of one stream (raw IMU row -> 25-float pose message).  A launch
+ * covers E = B streams x nF consecutive frames; estimate e = b * nF + f_rel, absolute frame
+ * f = frame0 + f_rel.  Frame-indexed device buffers are rings of `*_ring` frames per stream, slot
+ * f % ring; frames before 0 clamp to frame 0, which reproduces the reference's "repeat the first
+ * row / first prediction" warm-up (estimator.py:96-97, :114-115).
+ */
+#ifndef APE_B200_H
+#define APE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APE_OK 0
+#define APE_ERR_BAD_ARG 1        /* null pointer / size out of range */
+#define APE_ERR_UNSUPPORTED 2    /* shape not supported by this kernel (e.g. H % 32 != 0) */
+#define APE_ERR_CUDA 3           /* a CUDA runtime call failed; see ape_last_cuda_error() */
+#define APE_ERR_NO_SM100 4       /* the current device is not compute capability 10.x */
+
+/* estimator kinds: which parse_row_to_xx is followed */
+#define APE_KIND_WATCH_ONLY 0    /* estimate/watch_only.py:46-82            -> 20 features */
+#define APE_KIND_POCKET 1        /* estimate/watch_phone_pocket_nn.py:41-96  -> 22 features */
+#define APE_KIND_UARM 2          /* estimate/watch_phone_uarm_nn.py:43-105   -> 38 features */
+
+/* wire layouts of a raw row (data_types/messaging.py:20-68 and :96-187) */
+#define APE_LAYOUT_WATCH_ONLY 0  /* 28 floats */
+#define APE_LAYOUT_WATCH_PHONE 1 /* 55 floats */
+
+/* network target sets (utility/names.py:4-29) */
+#define APE_TARGET_ORI_CAL_LARM_UARM 0           /* O = 12 */
+#define APE_TARGET_ORI_CAL_LARM_UARM_HIPS 1      /* O = 14 */
+#define APE_TARGET_ORI_POS_CAL_LARM_UARM_HIPS 2  /* O = 20 */
+
+/* dropout mask source of the MC-LSTM */
+#define APE_MASK_NONE 0      /* eval mode: no dropout (DropoutLSTM.forward after .eval()) */
+#define APE_MASK_INJECTED 1  /* caller supplies the Bernoulli masks (bit-comparable parity runs) */
+#define APE_MASK_PHILOX 2    /* counter-based Philox4x32-10 keyed by (seed; stream, frame, sample, gap, t, unit) */
+
+/* ---- library / device ------------------------------------------------------------------------ */
+
+/* ABI version of this header (bumped on any signature change). */
+int ape_abi_version(void);
+/* cudaGetErrorString of the last failing CUDA call made by this library on the calling thread. */
+const char* ape_last_cuda_error(void);
+/* sm count / smem per block of the current device; returns APE_ERR_NO_SM100 off Blackwell. */
+int ape_device_info(int* sm_count, int* smem_optin_bytes, int* cc_major, int* cc_minor);
+/* number of floats of the packed weight blob (csrc/ape_lstm_pack.h) for a DropoutLSTM(I, H, L, O). */
+int ape_lstm_blob_floats(int I, int H, int L, int O, int64_t* floats);
+
+/* ---- stage 1: raw rows -> calibrated, normalised feature rows --------------------------------- */
+/*
+ * Replaces parse_row_to_xx (watch_only.py:46-82, watch_phone_pocket_nn.py:41-96,
+ * watch_phone_uarm_nn.py:43-105) and the z-score of estimator.py:103-104 for B x nF rows at once.
+ *   raw      [B][nF][ncols] float32, ncols = 28 (layout 0) or 55 (layout 1)
+ *   xx_m/s   [I] float64 column means / stds (data_stats pickles)
+ *   feats    [B][feat_ring][I] float32, row of absolute frame f written to slot f % feat_ring
+ *   normalize 0: write raw features (what parse_row_to_xx returns), 1: (xx - m) / s
+ * Arithmetic is float64 with the reference's float32 rounding point (watch_only.py:82) kept.
+ */
+int ape_features(const float* raw, int layout, int kind, const double* xx_m, const double* xx_s,
+                 int normalize, float* feats, int B, int nF, int frame0, int feat_ring, void* stream);
+
+/* ---- stage 2: MC-dropout LSTM regressor -------------------------------------------------------- */
+/*
+ * Replaces DropoutLSTM.forward / .monte_carlo_predictions (nn_models.py:180-207) and the
+ * "keep the last step" of make_prediction_from_row_hist (watch_only.py:84-97), batched over
+ * (estimates x MC samples).  Layer 0 runs once per estimate (no dropout in front of it), layers >= 1
+ * per (estimate, sample); the output layer is applied to the last step only unless all_steps != 0.
+ */
+typedef struct ape_lstm_args {
+    /* model: packed by arm_pose_estimation_b200.estimate.nn_models.pack_lstm_weights() */
+    const float* weights;      /* device blob, layout documented in csrc/ape_lstm_pack.h */
+    int I, H, L, T, O;         /* input, hidden, layers, sequence length, outputs */
+    float dropout_p;           /* Bernoulli drop probability of the inter-layer dropout */
+    /* input: exactly one of x_dense / feat_ring_buf is non-null */
+    const float* x_dense;      /* [E][T][I] normalised windows (DropoutLSTM.forward API) */
+    const float* feat_ring_buf;/* [B][feat_ring][I] ring written by ape_features */
+    int feat_ring;
+    int B, nF, frame0;         /* E = B * nF estimates */
+    int n_samples;             /* MC samples per estimate (rows of layers >= 1 = E * n_samples) */
+    /* dropout masks */
+    int mask_mode;             /* APE_MASK_* */
+    const uint8_t* masks;      /* APE_MASK_INJECTED: [E][L-1][T][n_samples][H] of {0,1}, else null */
+    uint64_t philox_seed;
+    uint32_t stream_id0;       /* global id of stream 0 of this launch (shard offset) */
+    /* workspace: ape_mc_lstm_workspace_bytes() bytes, 256-byte aligned */
+    void* workspace;
+    /* output */
+    float* preds;              /* all_steps == 0: [B][pred_ring][n_samples][O], slot f % pred_ring
+                                  all_steps != 0: [E][n_samples][T][O] */
+    int pred_ring;
+    int all_steps;
+    /* profiling: null, or L floats on the HOST - the call then brackets every layer launch with CUDA events,
+       synchronises the stream and writes each layer's device time in milliseconds (bench.py's roofline leg) */
+    float* layer_ms;
+} ape_lstm_args;
+
+int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
+/* fp32 FFMA variant (parity anchor; H in {32, 64, 128, 256}). */
+int ape_mc_lstm_fma(const ape_lstm_args* args, void* stream);
+/*
+ * The Bernoulli keep-masks APE_MASK_PHILOX draws, written out as bytes in the APE_MASK_INJECTED layout
+ * [E][L-1][T][n_samples][H] - lets a checker replay a Philox run through any injected-mask implementation.
+ */
+int ape_philox_masks(uint64_t philox_seed, uint32_t stream_id0, int B, int nF, int frame0, int L, int T,
+                     int n_samples, int H, float dropout_p, uint8_t* masks, void* stream);
+
+/* ---- stage 3: targets -> quaternions + forward kinematics + MC reduction ----------------------- */
+/*
+ * Replaces the de-normalisation of estimator.py:108-109, the smoothing stack of :112-118,
+ * estimate_joints.arm_pose_from_nn_targets (estimate_joints.py:16-92) and
+ * compose_msg.msg_from_nn_targets_est (compose_msg.py:13-108), plus the per-frame std over the
+ * S = smooth * n_samples rows (SURVEY.md §8a "new").
+ *   preds    [B][pred_ring][n_samples][O] float32 normalised network outputs
+ *   yy_m/s   [O] float32 (null: preds are already de-normalised)
+ *   body9    [9] float32: larm_vec, uarm_vec, uarm_orig_rh (estimator.py:57-68)
+ *   msg      [E][25] float32: [larm_q, hand, larm_q, elbow, uarm_q, shoulder, hips_q]
+ *   samples  [E][S][6] float32 or null: per-row hand xyz, elbow xyz (message tail of estimator.py:131-136)
+ *   stdev    [E][6] float32 or null: population std of those rows
+ *   est_rows [E][S][W] float32 or null: the full per-row output of arm_pose_from_nn_targets, W = 14 (target 0:
+ *            hand3, elbow3, larm_q4, uarm_q4) or 21 (targets 1, 2: hand3, elbow3, shoulder3, larm_q4, uarm_q4, hips_q4)
+ *   status   [E] int32 or null: 0 ok, 1 = a 6D pair was degenerate (the reference raises LinAlgError)
+ */
+int ape_fk_reduce(const float* preds, int pred_ring, const float* yy_m, const float* yy_s, const float* body9,
+                  int target, int O, int B, int nF, int frame0, int n_samples, int smooth,
+                  float* msg, float* samples, float* stdev, float* est_rows, int32_t* status, void* stream);
+
+/*
+ * compose_msg.msg_from_nn_targets_est (compose_msg.py:13-108) on rows that already hold quaternions + origins:
+ *   est [E][S][W] float32 rows as produced by arm_pose_from_nn_targets (W = 14 | 21, see est_rows above)
+ *   msg [E][25], stdev [E][6] or null
+ */
+int ape_msg_from_est(const float* est, int W, const float* body9, int target, int E, int S, float* msg,
+                     float* stdev, void* stream);
+
+/* ---- host self-check hooks (tests only; one row per call, never used by the product path) ------ */
+/* The __host__ __device__ row math of the kernels, compiled for the host so a CPU-only box can pin it. */
+int ape_selfcheck_philox(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4);
+int ape_selfcheck_keep8(uint64_t seed, uint32_t stream, uint32_t frame, uint32_t sample, uint32_t gap,
+                        uint32_t t, uint32_t group, float dropout_p, uint32_t* keep_bits);
+int ape_selfcheck_features(int kind, int layout, const float* row, double* xx, int* n_features);
+int ape_selfcheck_row_pose(int target, const double* preds, const double* body9, int use_float, double* est, int* bad);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APE_B200_H */
