@@ -24,7 +24,7 @@ KSLICE = 16                      # csrc/ape_lstm_pack.h: APE_KSLICE
 SYMBOLS = (
     "ape_abi_version", "ape_last_cuda_error", "ape_device_info", "ape_lstm_blob_floats", "ape_features",
     "ape_mc_lstm_workspace_bytes", "ape_mc_lstm_fma", "ape_philox_masks", "ape_fk_reduce", "ape_msg_from_est",
-    "ape_selfcheck_philox", "ape_selfcheck_keep8", "ape_selfcheck_features", "ape_selfcheck_row_pose",
+    "ape_selfcheck_philox", "ape_selfcheck_keep8", "ape_selfcheck_features", "ape_selfcheck_row_pose", "ape_selftest_umma",
 )
 
 
@@ -98,6 +98,8 @@ def load():
     lib.ape_selfcheck_features.argtypes = [i32, i32, C.POINTER(f32), C.POINTER(C.c_double), C.POINTER(i32)]
     lib.ape_selfcheck_row_pose.restype = i32
     lib.ape_selfcheck_row_pose.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double), i32, C.POINTER(C.c_double), C.POINTER(i32)]
+    lib.ape_selftest_umma.restype = i32
+    lib.ape_selftest_umma.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     _lib = lib
     return lib
 

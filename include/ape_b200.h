@@ -152,6 +152,9 @@ int ape_selfcheck_keep8(uint64_t seed, uint32_t stream, uint32_t frame, uint32_t
                         uint32_t t, uint32_t group, float dropout_p, uint32_t* keep_bits);
 int ape_selfcheck_features(int kind, int layout, const float* row, double* xx, int* n_features);
 int ape_selfcheck_row_pose(int target, const double* preds, const double* body9, int use_float, double* est, int* bad);
+/* GPU self-test of the tcgen05 / TMEM plumbing: D[128*cta_group][N] (f32) = A * B^T with f16 operands packed in the
+ * canonical K-major no-swizzle layout of csrc/ape_umma.cuh (a_packed: [cta][K/8][128][8], b_packed: [cta][K/8][N/cta][8]). */
+int ape_selftest_umma(const void* a_packed, const void* b_packed, float* d, int N, int K, int cta_group, void* stream);
 
 #ifdef __cplusplus
 }

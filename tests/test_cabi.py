@@ -74,7 +74,7 @@ def test_product_package_never_touches_oracle_or_selfcheck_hooks():
         src = py.read_text()
         assert "import oracle" not in src and "from oracle" not in src, py
         if py.name != "_native.py":
-            assert "ape_selfcheck" not in src, py
+            assert "ape_selfcheck" not in src and "ape_selftest" not in src, py
 
 
 def test_sass_is_sm100a():
