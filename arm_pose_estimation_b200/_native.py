@@ -23,7 +23,8 @@ KSLICE = 16                      # csrc/ape_lstm_pack.h: APE_KSLICE
 # every symbol include/ape_b200.h declares (tests/test_cabi.py checks the header against this list and the .so)
 SYMBOLS = (
     "ape_abi_version", "ape_last_cuda_error", "ape_device_info", "ape_lstm_blob_floats", "ape_features",
-    "ape_mc_lstm_workspace_bytes", "ape_mc_lstm_fma", "ape_philox_masks", "ape_fk_reduce", "ape_msg_from_est",
+    "ape_mc_lstm_workspace_bytes", "ape_mc_lstm_fma", "ape_mc_lstm_tc_supported", "ape_lstm_tc_blob_bytes",
+    "ape_mc_lstm_tc_workspace_bytes", "ape_mc_lstm_tc", "ape_philox_masks", "ape_fk_reduce", "ape_msg_from_est",
     "ape_selfcheck_philox", "ape_selfcheck_keep8", "ape_selfcheck_features", "ape_selfcheck_row_pose", "ape_selftest_umma",
 )
 
@@ -47,6 +48,7 @@ class LstmArgs(C.Structure):
         ("preds", C.c_void_p),
         ("pred_ring", C.c_int),
         ("all_steps", C.c_int),
+        ("weights_tc", C.c_void_p),
         ("layer_ms", C.c_void_p),
     ]
 
@@ -83,6 +85,14 @@ def load():
     lib.ape_mc_lstm_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(u64)]
     lib.ape_mc_lstm_fma.restype = i32
     lib.ape_mc_lstm_fma.argtypes = [C.POINTER(LstmArgs), vp]
+    lib.ape_mc_lstm_tc_supported.restype = i32
+    lib.ape_mc_lstm_tc_supported.argtypes = [i32]
+    lib.ape_lstm_tc_blob_bytes.restype = i32
+    lib.ape_lstm_tc_blob_bytes.argtypes = [i32, i32, C.POINTER(C.c_int64)]
+    lib.ape_mc_lstm_tc_workspace_bytes.restype = i32
+    lib.ape_mc_lstm_tc_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(u64)]
+    lib.ape_mc_lstm_tc.restype = i32
+    lib.ape_mc_lstm_tc.argtypes = [C.POINTER(LstmArgs), vp]
     lib.ape_philox_masks.restype = i32
     lib.ape_philox_masks.argtypes = [u64, u32, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp]
     lib.ape_fk_reduce.restype = i32
@@ -136,7 +146,20 @@ def blob_floats(I, H, L, O):
     return out.value
 
 
-def workspace_bytes(I, H, L, T, O, E, n):
+def workspace_bytes(I, H, L, T, O, E, n, tensor_core=False):
     out = C.c_uint64(0)
-    check(load().ape_mc_lstm_workspace_bytes(I, H, L, T, O, E, n, C.byref(out)), "ape_mc_lstm_workspace_bytes")
+    if tensor_core:
+        check(load().ape_mc_lstm_tc_workspace_bytes(I, H, L, T, O, E, n, C.byref(out)), "ape_mc_lstm_tc_workspace_bytes")
+    else:
+        check(load().ape_mc_lstm_workspace_bytes(I, H, L, T, O, E, n, C.byref(out)), "ape_mc_lstm_workspace_bytes")
+    return out.value
+
+
+def tc_supported(H, L):
+    return L >= 2 and bool(load().ape_mc_lstm_tc_supported(H))
+
+
+def tc_blob_bytes(H, L):
+    out = C.c_int64(0)
+    check(load().ape_lstm_tc_blob_bytes(H, L, C.byref(out)), "ape_lstm_tc_blob_bytes")
     return out.value

@@ -9,6 +9,7 @@
 // tile-local K-major layout [tile][T][H][R] so both sides move float4s with unit stride.
 #include "ape_common.cuh"
 #include "ape_lstm_pack.h"
+#include "ape_lstm_plan.cuh"
 
 namespace ape {
 
@@ -295,12 +296,7 @@ static size_t layer_smem_bytes(int rt, int H, int kin_pad) {
 static long long tiles_of(long long rows, int rt) { return (rows + 16 * rt - 1) / (16 * rt); }
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-struct FmaPlan {
-    int rt0, rt1;
-    long long tiles0, tiles1;
-    size_t seq0_bytes, seq1_bytes, total;
-};
-static int make_plan(int I, int H, int L, int T, long long E, int n, FmaPlan* p) {
+int make_plan(int I, int H, int L, int T, long long E, int n, FmaPlan* p) {
     if (H % CHUNK_UNITS != 0 || H < CHUNK_UNITS) return APE_ERR_UNSUPPORTED;
     const int kp0 = ape_pack_kin_pad(0, I, H);
     if (max_rt_for(H, kp0 > H ? kp0 : H) == 0) return APE_ERR_UNSUPPORTED;
@@ -326,6 +322,58 @@ static int launch_layer_rt(int rt, const LayerArgs& a, long long tiles, cudaStre
     return launch_layer<1>(a, tiles, st);
 }
 
+int check_lstm_args(const ape_lstm_args* g) {
+    if (!g || !g->weights || !g->preds) return APE_ERR_BAD_ARG;
+    if (g->I < 1 || g->H < 1 || g->L < 1 || g->T < 1 || g->O < 1 || g->B < 0 || g->nF < 0 || g->n_samples < 1) return APE_ERR_BAD_ARG;
+    if ((g->x_dense == nullptr) == (g->feat_ring_buf == nullptr)) return APE_ERR_BAD_ARG;
+    if (g->feat_ring_buf && (g->feat_ring < g->nF + g->T - 1 || g->frame0 < 0)) return APE_ERR_BAD_ARG;
+    if (!g->all_steps && (g->pred_ring < g->nF || g->pred_ring < 1)) return APE_ERR_BAD_ARG;
+    if (g->all_steps && g->L == 1 && g->n_samples > 1) return APE_ERR_UNSUPPORTED;
+    if (g->mask_mode < APE_MASK_NONE || g->mask_mode > APE_MASK_PHILOX) return APE_ERR_BAD_ARG;
+    if (g->mask_mode == APE_MASK_INJECTED && g->L > 1 && !g->masks) return APE_ERR_BAD_ARG;
+    if (g->mask_mode != APE_MASK_NONE && !(g->dropout_p >= 0.0f && g->dropout_p < 1.0f)) return APE_ERR_BAD_ARG;
+    if ((long long)g->B * g->nF * g->n_samples > 0x7fffffffLL) return APE_ERR_BAD_ARG;
+    return APE_OK;
+}
+
+// one layer of the fp32 path; `seq_in` / `seq_out` are the inter-layer sequence buffers (null where unused)
+int fma_launch_layer(const ape_lstm_args* g, int l, const FmaPlan& p, const float* seq_in, float* seq_out, cudaStream_t st) {
+    const long long E = (long long)g->B * g->nF;
+    const bool last = l == g->L - 1;
+    LayerArgs a{};
+    a.Wp = g->weights + ape_pack_layer_offset(l, g->I, g->H);
+    a.bp = g->weights + ape_pack_bias_offset(l, g->I, g->H);
+    a.Kin = l == 0 ? g->I : g->H;
+    a.Kin_pad = ape_pack_kin_pad(l, g->I, g->H);
+    a.H = g->H; a.T = g->T;
+    a.feat_ring = g->feat_ring; a.nF = g->nF; a.frame0 = g->frame0;
+    a.mask_mode = l == 0 ? APE_MASK_NONE : g->mask_mode;
+    a.masks = g->masks; a.gap = l - 1; a.n_gaps = g->L - 1;
+    a.seed = g->philox_seed; a.stream_id0 = g->stream_id0;
+    a.keep_scale = g->mask_mode == APE_MASK_NONE ? 1.0f : 1.0f / (1.0f - g->dropout_p);
+    a.keep_thr16 = keep_threshold16(g->dropout_p);
+    a.Wo = g->weights + ape_pack_out_offset(g->I, g->H, g->L);
+    a.bo = a.Wo + (size_t)g->O * g->H;
+    a.O = g->O;
+    a.pred_ring = g->pred_ring; a.all_steps = g->all_steps; a.n_out = g->n_samples;
+    int rt; long long tiles;
+    if (l == 0) {
+        a.in_mode = g->x_dense ? IN_DENSE : IN_WINDOW;
+        a.in = g->x_dense ? g->x_dense : g->feat_ring_buf;
+        a.rows = (int)E; a.n = 1;
+        rt = p.rt0; tiles = p.tiles0;
+    } else {
+        a.in_mode = l == 1 ? IN_SHARED : IN_TILED;
+        a.in = seq_in;
+        a.in_R = 16 * p.rt0;
+        a.rows = (int)(E * g->n_samples); a.n = g->n_samples;
+        rt = p.rt1; tiles = p.tiles1;
+    }
+    a.out_seq = last ? nullptr : seq_out;
+    a.preds = last ? g->preds : nullptr;
+    return launch_layer_rt(rt, a, tiles, st);
+}
+
 }  // namespace ape
 
 extern "C" int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes) {
@@ -340,19 +388,12 @@ extern "C" int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, in
 
 extern "C" int ape_mc_lstm_fma(const ape_lstm_args* g, void* stream) {
     using namespace ape;
-    if (!g || !g->weights || !g->preds) return APE_ERR_BAD_ARG;
-    if (g->I < 1 || g->H < 1 || g->L < 1 || g->T < 1 || g->O < 1 || g->B < 0 || g->nF < 0 || g->n_samples < 1) return APE_ERR_BAD_ARG;
-    if ((g->x_dense == nullptr) == (g->feat_ring_buf == nullptr)) return APE_ERR_BAD_ARG;
-    if (g->feat_ring_buf && (g->feat_ring < g->nF + g->T - 1 || g->frame0 < 0)) return APE_ERR_BAD_ARG;
-    if (!g->all_steps && (g->pred_ring < g->nF || g->pred_ring < 1)) return APE_ERR_BAD_ARG;
-    if (g->mask_mode < APE_MASK_NONE || g->mask_mode > APE_MASK_PHILOX) return APE_ERR_BAD_ARG;
-    if (g->mask_mode == APE_MASK_INJECTED && g->L > 1 && !g->masks) return APE_ERR_BAD_ARG;
-    if (g->mask_mode != APE_MASK_NONE && !(g->dropout_p >= 0.0f && g->dropout_p < 1.0f)) return APE_ERR_BAD_ARG;
+    int rc = check_lstm_args(g);
+    if (rc != APE_OK) return rc;
     const long long E = (long long)g->B * g->nF;
     if (E == 0) return APE_OK;
-    if (E * g->n_samples > 0x7fffffffLL) return APE_ERR_BAD_ARG;
     FmaPlan p;
-    int rc = make_plan(g->I, g->H, g->L, g->T, E, g->n_samples, &p);
+    rc = make_plan(g->I, g->H, g->L, g->T, E, g->n_samples, &p);
     if (rc != APE_OK) return rc;
     if (p.total > 0 && !g->workspace) return APE_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -367,40 +408,9 @@ extern "C" int ape_mc_lstm_fma(const ape_lstm_args* g, void* stream) {
     if (prof) APE_CUDA_TRY(cudaEventRecord(ev[0], st));
 
     for (int l = 0; l < g->L; ++l) {
-        const bool last = l == g->L - 1;
-        LayerArgs a{};
-        a.Wp = g->weights + ape_pack_layer_offset(l, g->I, g->H);
-        a.bp = g->weights + ape_pack_bias_offset(l, g->I, g->H);
-        a.Kin = l == 0 ? g->I : g->H;
-        a.Kin_pad = ape_pack_kin_pad(l, g->I, g->H);
-        a.H = g->H; a.T = g->T;
-        a.feat_ring = g->feat_ring; a.nF = g->nF; a.frame0 = g->frame0;
-        a.mask_mode = l == 0 ? APE_MASK_NONE : g->mask_mode;
-        a.masks = g->masks; a.gap = l - 1; a.n_gaps = g->L - 1;
-        a.seed = g->philox_seed; a.stream_id0 = g->stream_id0;
-        a.keep_scale = g->mask_mode == APE_MASK_NONE ? 1.0f : 1.0f / (1.0f - g->dropout_p);
-        a.keep_thr16 = keep_threshold16(g->dropout_p);
-        a.Wo = g->weights + ape_pack_out_offset(g->I, g->H, g->L);
-        a.bo = a.Wo + (size_t)g->O * g->H;
-        a.O = g->O;
-        a.pred_ring = g->pred_ring; a.all_steps = g->all_steps; a.n_out = g->n_samples;
-        int rt; long long tiles;
-        if (l == 0) {
-            a.in_mode = g->x_dense ? IN_DENSE : IN_WINDOW;
-            a.in = g->x_dense ? g->x_dense : g->feat_ring_buf;
-            a.rows = (int)E; a.n = 1;
-            rt = p.rt0; tiles = p.tiles0;
-            a.out_seq = last ? nullptr : seq0;
-        } else {
-            a.in_mode = l == 1 ? IN_SHARED : IN_TILED;
-            a.in = l == 1 ? seq0 : seq1[(l - 2) & 1];
-            a.in_R = 16 * p.rt0;
-            a.rows = (int)(E * g->n_samples); a.n = g->n_samples;
-            rt = p.rt1; tiles = p.tiles1;
-            a.out_seq = last ? nullptr : seq1[(l - 1) & 1];
-        }
-        a.preds = last ? g->preds : nullptr;
-        rc = launch_layer_rt(rt, a, tiles, st);
+        const float* seq_in = l == 0 ? nullptr : (l == 1 ? seq0 : seq1[(l - 2) & 1]);
+        float* seq_out = l == 0 ? seq0 : seq1[(l - 1) & 1];
+        rc = fma_launch_layer(g, l, p, seq_in, seq_out, st);
         if (rc != APE_OK) return rc;
         if (prof) APE_CUDA_TRY(cudaEventRecord(ev[l + 1], st));
     }

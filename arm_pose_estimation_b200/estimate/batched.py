@@ -63,7 +63,8 @@ class EstimateBatch:
 class BatchedEstimator:
     def __init__(self, kind, layout, state, seq_len, y_targets, stats, n_streams, mc_samples,
                  smooth=1, dropout=0.2, bonemap=None, frames_per_call=1, emit_samples=True, normalize=True,
-                 mask_mode=N.MASK_PHILOX, philox_seed=0, first_stream=0, device=None):
+                 mask_mode=N.MASK_PHILOX, philox_seed=0, first_stream=0, device=None,
+                 lstm_variant="auto", tc_min_rows=4096, tc_tolerance_m=5e-5):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedEstimator needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = N.load()
@@ -113,8 +114,62 @@ class BatchedEstimator:
             self.std_host = torch.zeros((B, nF, 6), dtype=f32).pin_memory()
             self.samples_host = torch.zeros((B, nF, self.S, 6), dtype=f32).pin_memory() if emit_samples else None
             self.status_host = torch.zeros((B, nF), dtype=torch.int32).pin_memory()
+            # ---- which LSTM kernel: fp32 FFMA (exact) or tcgen05 fp16-operand tensor cores ----------------------
+            # Tensor cores only when the streams x MC-samples batch is a real dense contraction AND the fp16-operand
+            # result stays within tc_tolerance_m of the fp32 kernel on a probe batch of THIS model's weights.
+            self.tc_weights = None
+            self.tc_probe_error_m = None
+            self.lstm_variant = "fp32"
+            if lstm_variant not in ("auto", "fp32", "tc"):
+                raise UserWarning(f"lstm_variant must be 'auto', 'fp32' or 'tc', got {lstm_variant!r}")
+            tc_ok = N.tc_supported(self.H, self.L)
+            if lstm_variant == "tc" and not tc_ok:
+                raise UserWarning(f"the tensor-core LSTM kernel does not support H={self.H}, L={self.L}")
+            if lstm_variant == "tc" or (lstm_variant == "auto" and tc_ok and B * nF * self.n >= tc_min_rows):
+                self.tc_weights = torch.from_numpy(nn_models.pack_lstm_weights_tc(state)).to(dev)
+                assert self.tc_weights.numel() == N.tc_blob_bytes(self.H, self.L)
+                ws_tc = N.workspace_bytes(self.I, self.H, self.L, self.T, self.O, B * nF, self.n, tensor_core=True) + 3 * 256 * self.T * self.H * 4
+                if ws_tc > self.workspace.numel():
+                    self.workspace = torch.empty(ws_tc, dtype=torch.uint8, device=dev)
+                self.tc_probe_error_m = self._probe_tc_error()
+                if lstm_variant == "tc" or self.tc_probe_error_m <= tc_tolerance_m:
+                    self.lstm_variant = "tc"
         self.frame = 0
         self.launches = 0             # kernels launched so far (bench.py reports it)
+
+    def _lstm_fn(self, variant=None):
+        return self.lib.ape_mc_lstm_tc if (variant or self.lstm_variant) == "tc" else self.lib.ape_mc_lstm_fma
+
+    def _probe_tc_error(self, n_est=16, n_samples=64):
+        """Max |position| difference (metres) between the tensor-core and the fp32 LSTM kernels on a probe batch:
+        N(0,1) normalised windows, the same Philox masks for both (the keying does not depend on the kernel)."""
+        dev = self.device
+        g = torch.Generator(device="cpu").manual_seed(1234)
+        x = torch.randn((n_est, self.T, self.I), generator=g, dtype=torch.float32).to(dev)
+        ws = torch.empty(max(N.workspace_bytes(self.I, self.H, self.L, self.T, self.O, n_est, n_samples),
+                             N.workspace_bytes(self.I, self.H, self.L, self.T, self.O, n_est, n_samples, tensor_core=True)),
+                         dtype=torch.uint8, device=dev)
+        outs = []
+        for variant in ("fp32", "tc"):
+            preds = torch.zeros((n_est, 1, n_samples, self.O), dtype=torch.float32, device=dev)
+            a = N.LstmArgs()
+            a.weights, a.weights_tc = self.weights.data_ptr(), self.tc_weights.data_ptr()
+            a.I, a.H, a.L, a.T, a.O = self.I, self.H, self.L, self.T, self.O
+            a.dropout_p = self.p
+            a.x_dense, a.feat_ring_buf, a.feat_ring = x.data_ptr(), None, 0
+            a.B, a.nF, a.frame0, a.n_samples = n_est, 1, 0, n_samples
+            a.mask_mode, a.philox_seed, a.stream_id0 = N.MASK_PHILOX, 0x5EED, 0
+            a.workspace = ws.data_ptr()
+            a.preds, a.pred_ring, a.all_steps = preds.data_ptr(), 1, 0
+            N.check(self._lstm_fn(variant)(a, N.current_stream_ptr()), f"ape_mc_lstm ({variant} probe)")
+            est = torch.empty((n_est, n_samples, EST_WIDTH[self.target]), dtype=torch.float32, device=dev)
+            msg = torch.empty((n_est, 25), dtype=torch.float32, device=dev)
+            N.check(self.lib.ape_fk_reduce(N.ptr(preds), 1, N.ptr(self.yy_m), N.ptr(self.yy_s), N.ptr(self.body), self.target,
+                                           self.O, n_est, 1, 0, n_samples, 1, N.ptr(msg), None, None, N.ptr(est), None,
+                                           N.current_stream_ptr()), "ape_fk_reduce (probe)")
+            outs.append(est[..., :9 if EST_WIDTH[self.target] == 21 else 6].clone())
+        torch.cuda.current_stream().synchronize()
+        return float((outs[0] - outs[1]).abs().max().item())
 
     def reset(self):
         """Forget all history, like ``Estimator.reset`` (estimator.py:88-91): the next row is frame 0 again."""
@@ -151,9 +206,10 @@ class BatchedEstimator:
         a.philox_seed, a.stream_id0 = self.philox_seed, self.first_stream
         a.workspace = self.workspace.data_ptr()
         a.preds, a.pred_ring, a.all_steps = self.preds.data_ptr(), self.pred_ring, 0
+        a.weights_tc = None if self.tc_weights is None else self.tc_weights.data_ptr()
         if layer_ms is not None:                     # profiling leg: float32 host array of L entries, filled on return
             a.layer_ms = layer_ms.ctypes.data
-        N.check(lib.ape_mc_lstm_fma(a, st), "ape_mc_lstm")
+        N.check(self._lstm_fn()(a, st), "ape_mc_lstm")
         N.check(lib.ape_fk_reduce(N.ptr(self.preds), self.pred_ring, N.ptr(self.yy_m), N.ptr(self.yy_s), N.ptr(self.body),
                                   self.target, self.O, B, nF, self.frame, self.n, self.smooth,
                                   N.ptr(self.msg), N.ptr(self.samples), N.ptr(self.std), None, N.ptr(self.status), st),

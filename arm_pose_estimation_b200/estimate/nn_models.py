@@ -51,6 +51,38 @@ def pack_lstm_weights(state):
     return np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
 
 
+def pack_lstm_weights_tc(state):
+    """Reference state dict -> the fp16 blob of the tensor-core path (``csrc/ape_lstm_tc.cu``), as uint8 bytes.
+
+    Per layer l >= 1: for each CTA r of the pair, for each part (input weights, recurrent weights), for each chunk
+    c of 32 hidden units, the 64 gate columns  n = 64 r + nl  of the chunk's 128 (n = 4 * u_local + g, i.e. units
+    16 r .. 16 r + 15, gates i, f, g, o interleaved) as a K-major no-swizzle tile ``[H/8][64][8]`` halfs; then the
+    bias ``b_ih + b_hh`` in column order 4u + g, pre-multiplied by -log2(e) (i, f, o) or -2 log2(e) (g) so the
+    epilogue's sigmoid / tanh arguments come out of one FMA."""
+    st = {k: np.asarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
+          for k, v in state.items()}
+    I, H, L, O = lstm_dims(st)
+    log2e = np.float32(1.4426950408889634)
+    parts = []
+    nl = np.arange(64)
+    for l in range(1, L):
+        mats = (st[f"lstm.weight_ih_l{l}"], st[f"lstm.weight_hh_l{l}"])
+        for r in range(2):
+            n = 64 * r + nl
+            for w in mats:
+                for c in range(H // 32):
+                    rows = (n % 4) * H + 32 * c + n // 4
+                    tile = w[rows].astype(np.float16)                               # [64, H]
+                    parts.append(np.ascontiguousarray(tile.reshape(64, H // 8, 8).transpose(1, 0, 2)).view(np.uint8).ravel())
+        bias = (st[f"lstm.bias_ih_l{l}"] + st[f"lstm.bias_hh_l{l}"]).reshape(4, H).T.copy()       # [u][g]
+        bias *= -log2e
+        bias[:, 2] *= np.float32(2.0)
+        parts.append(np.ascontiguousarray(bias.reshape(-1), dtype=np.float32).view(np.uint8))
+    if not parts:
+        return np.zeros(0, np.uint8)
+    return np.ascontiguousarray(np.concatenate(parts))
+
+
 def packed_floats(I, H, L, O):
     """Python mirror of ``ape_pack_total_floats`` (checked against the library in tests/test_cabi.py)."""
     kin0 = -(-I // N.KSLICE) * N.KSLICE

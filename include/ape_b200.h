@@ -102,6 +102,9 @@ typedef struct ape_lstm_args {
                                   all_steps != 0: [E][n_samples][T][O] */
     int pred_ring;
     int all_steps;
+    /* tensor-core path only: fp16 gate weights of layers >= 1 packed by pack_lstm_weights_tc()
+       (ape_lstm_tc_blob_bytes() bytes, layout in csrc/ape_lstm_tc.cu); ignored by ape_mc_lstm_fma */
+    const void* weights_tc;
     /* profiling: null, or L floats on the HOST - the call then brackets every layer launch with CUDA events,
        synchronises the stream and writes each layer's device time in milliseconds (bench.py's roofline leg) */
     float* layer_ms;
@@ -110,6 +113,15 @@ typedef struct ape_lstm_args {
 int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
 /* fp32 FFMA variant (parity anchor; H in {32, 64, 128, 256}). */
 int ape_mc_lstm_fma(const ape_lstm_args* args, void* stream);
+/*
+ * Tensor-core variant (tcgen05, cta_group::2, TMEM accumulators): layer 0 in fp32, layers >= 1 with fp16 operands
+ * and fp32 accumulation.  H in {64, 128}, L >= 2; same arguments and outputs as ape_mc_lstm_fma plus weights_tc.
+ * Use when the streams x MC-samples batch is large (>= a few thousand rows); the fp32 variant is the exact path.
+ */
+int ape_mc_lstm_tc_supported(int H);
+int ape_lstm_tc_blob_bytes(int H, int L, int64_t* bytes);
+int ape_mc_lstm_tc_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
+int ape_mc_lstm_tc(const ape_lstm_args* args, void* stream);
 /*
  * The Bernoulli keep-masks APE_MASK_PHILOX draws, written out as bytes in the APE_MASK_INJECTED layout
  * [E][L-1][T][n_samples][H] - lets a checker replay a Philox run through any injected-mask implementation.

@@ -1,0 +1,86 @@
+"""GPU (-m gpu): the tcgen05 tensor-core LSTM path (fp16 operands, fp32 accumulate) against the oracle, the golden
+reference messages and the fp32 kernel.  Tolerance: 1e-4 m on positions (north_star's bound); measured errors are
+printed - with the seeded weights they are ~5e-6 m."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, unpack_masks
+from arm_pose_estimation_b200 import _native as N
+from arm_pose_estimation_b200 import synthetic as syn
+from arm_pose_estimation_b200.estimate import batched
+from arm_pose_estimation_b200.utility.names import NNS_TARGETS
+from oracle import estimator as OE
+from test_gpu_parity import make_batched, msg_close, POS_TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def make(kind, B, n, variant, **kw):
+    spec = syn.kind_spec(kind)
+    state = kw.pop("state", None) or syn.synth_state_dict(spec["I"], spec["H"], spec["L"], spec["O"], 1234 + kind)
+    return batched.BatchedEstimator(kind=kind, layout=spec["layout"], state=state, seq_len=spec["T"], y_targets=spec["y_targets"],
+                                    stats=spec["stats"], n_streams=B, mc_samples=n, dropout=spec["p"], lstm_variant=variant,
+                                    **kw), spec, state
+
+
+@pytest.mark.parametrize("name", ["uarm_s1", "uarm_s4"])
+def test_tc_whole_path_against_reference_messages(name):
+    g = load_golden(f"e2e_{name}.npz")
+    n, smooth = int(g["n"]), int(g["smooth"])
+    masks = unpack_masks(g)
+    rows, F = g["rows"], len(g["rows"])
+    be, spec, _ = make(syn.KIND_UARM, 1, n, "tc", smooth=smooth, frames_per_call=F, mask_mode=N.MASK_INJECTED)
+    assert be.lstm_variant == "tc"
+    out = be.step(rows[None], masks=masks[None])
+    worst = msg_close(out.msg[0], g["msgs"][:, :25])
+    err = np.abs(out.samples[0].reshape(F, -1) - g["msgs"][:, 25:]).max()
+    assert err <= POS_TOL
+    print(f"{name} tensor-core path: worst position error vs the reference's messages {max(worst, err):.3g} m (probe {be.tc_probe_error_m:.3g} m)")
+
+
+def test_tc_small_hidden_size_and_ragged_rows_against_oracle():
+    # H = 64, L = 3 model on the uarm feature layout; 3 streams x 2 frames x 70 samples = 420 rows (not a multiple of 256)
+    kind, B, nF, n = syn.KIND_UARM, 3, 2, 70
+    state = syn.synth_state_dict(38, 64, 3, 12, 5)
+    be, spec, _ = make(kind, B, n, "tc", state=state, frames_per_call=nF, mask_mode=N.MASK_INJECTED)
+    rng = np.random.default_rng(1)
+    rows = syn.synth_rows(kind, B, nF, config_id=41)
+    masks = (rng.random(size=(B, nF, 2, spec["T"], n, 64)) < 0.8).astype(np.uint8)
+    out = be.step(rows, masks=masks)
+    for b in range(B):
+        orc = OE.OracleEstimator("uarm", spec["lookup"], state, spec["stats"], spec["y_targets"].name, spec["T"], 1, n, None,
+                                 spec["p"], mask_source=lambda f, b=b: list(masks[b, f]))
+        for f in range(nF):
+            want = np.asarray(orc.step(rows[b, f]))
+            msg_close(out.msg[b, f], want[:25])
+            assert np.abs(out.samples[b, f].ravel() - want[25:]).max() <= POS_TOL
+
+
+def test_tc_matches_fp32_kernel_on_many_tiles_with_philox():
+    # 200 streams x 100 samples = 20000 rows = 79 pair tiles > 74 clusters: the persistent tile loop wraps
+    kind, B, n = syn.KIND_UARM, 200, 100
+    rows = np.tile(syn.synth_rows(kind, 8, 3, config_id=5), (25, 1, 1))
+    a, _, _ = make(kind, B, n, "tc", mask_mode=N.MASK_PHILOX, philox_seed=77)
+    b, _, _ = make(kind, B, n, "fp32", mask_mode=N.MASK_PHILOX, philox_seed=77)
+    worst = 0.0
+    for f in range(3):
+        oa, ob = a.step(rows[:, f:f + 1]), b.step(rows[:, f:f + 1])
+        worst = max(worst, float(np.abs(oa.samples - ob.samples).max()), msg_close(oa.msg, ob.msg))
+        np.testing.assert_allclose(oa.std, ob.std, rtol=0.02, atol=2e-6)
+    print(f"tensor-core vs fp32 kernel, same Philox masks, 20000 rows x 3 frames: worst position difference {worst:.3g} m")
+    assert worst <= POS_TOL
+    # determinism of the tensor-core path
+    a2, _, _ = make(kind, B, n, "tc", mask_mode=N.MASK_PHILOX, philox_seed=77)
+    np.testing.assert_array_equal(a2.step(rows[:, 0:1]).msg, make(kind, B, n, "tc", mask_mode=N.MASK_PHILOX, philox_seed=77)[0].step(rows[:, 0:1]).msg)
+
+
+def test_auto_variant_selection():
+    small, _, _ = make(syn.KIND_UARM, 1, 100, "auto")                   # 100 rows: not a dense contraction -> fp32 FFMA
+    assert small.lstm_variant == "fp32"
+    big, _, _ = make(syn.KIND_UARM, 256, 100, "auto")                   # 25600 rows -> tensor cores, if the probe passes
+    assert big.lstm_variant == "tc" and big.tc_probe_error_m <= 5e-5
+    wide, _, _ = make(syn.KIND_POCKET, 256, 100, "auto")                # H = 256: not supported by the pair kernel -> fp32
+    assert wide.lstm_variant == "fp32"
+    with pytest.raises(UserWarning):
+        make(syn.KIND_POCKET, 4, 10, "tc")
