@@ -86,9 +86,9 @@ def load():
     lib.ape_mc_lstm_fma.restype = i32
     lib.ape_mc_lstm_fma.argtypes = [C.POINTER(LstmArgs), vp]
     lib.ape_mc_lstm_tc_supported.restype = i32
-    lib.ape_mc_lstm_tc_supported.argtypes = [i32]
+    lib.ape_mc_lstm_tc_supported.argtypes = [i32, i32, i32, i32]
     lib.ape_lstm_tc_blob_bytes.restype = i32
-    lib.ape_lstm_tc_blob_bytes.argtypes = [i32, i32, C.POINTER(C.c_int64)]
+    lib.ape_lstm_tc_blob_bytes.argtypes = [i32, i32, i32, C.POINTER(C.c_int64)]
     lib.ape_mc_lstm_tc_workspace_bytes.restype = i32
     lib.ape_mc_lstm_tc_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(u64)]
     lib.ape_mc_lstm_tc.restype = i32
@@ -155,11 +155,11 @@ def workspace_bytes(I, H, L, T, O, E, n, tensor_core=False):
     return out.value
 
 
-def tc_supported(H, L):
-    return L >= 2 and bool(load().ape_mc_lstm_tc_supported(H))
+def tc_supported(I, H, L, O):
+    return bool(load().ape_mc_lstm_tc_supported(I, H, L, O))
 
 
-def tc_blob_bytes(H, L):
+def tc_blob_bytes(I, H, L):
     out = C.c_int64(0)
-    check(load().ape_lstm_tc_blob_bytes(H, L, C.byref(out)), "ape_lstm_tc_blob_bytes")
+    check(load().ape_lstm_tc_blob_bytes(I, H, L, C.byref(out)), "ape_lstm_tc_blob_bytes")
     return out.value

@@ -53,14 +53,9 @@ template <typename F> APE_HD Quat<F> android_swap(const Quat<F>& q) { return {-q
 struct Philox4 { uint32_t v[4]; };
 
 APE_HD void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-#ifdef __CUDA_ARCH__
-    lo = a * b;
-    hi = __umulhi(a, b);
-#else
-    uint64_t p = (uint64_t)a * (uint64_t)b;
+    const uint64_t p = (uint64_t)a * (uint64_t)b;          // one IMAD.WIDE.U32 on the device
     lo = (uint32_t)p;
     hi = (uint32_t)(p >> 32);
-#endif
 }
 
 APE_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
@@ -93,6 +88,19 @@ APE_HD uint32_t philox_keep8(uint64_t seed, uint32_t stream, uint32_t frame, uin
     }
     return bits;
 }
+
+#ifdef __CUDACC__
+// The same draw as philox_keep8, returned as four half2 AND-masks (0xFFFF per kept 16-bit lane: unit 2i in the low
+// half of word i, unit 2i+1 in the high half) so fp16 operand units can be masked without unpacking.
+__device__ __forceinline__ uint4 philox_keep_halfmask(uint64_t seed, uint32_t stream, uint32_t frame, uint32_t sample,
+                                                      uint32_t gap, uint32_t t, uint32_t group, uint32_t keep_thr16) {
+    if (keep_thr16 >= 65536u) return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    const Philox4 r = philox4x32_10(stream, frame, (sample & 0xFFFFFu) | ((gap & 0xFu) << 20) | ((t & 0xFFu) << 24), group,
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t thr2 = keep_thr16 | (keep_thr16 << 16);
+    return make_uint4(__vcmpltu2(r.v[0], thr2), __vcmpltu2(r.v[1], thr2), __vcmpltu2(r.v[2], thr2), __vcmpltu2(r.v[3], thr2));
+}
+#endif
 
 APE_HD uint32_t keep_threshold16(float p) {
     float k = (1.0f - p) * 65536.0f + 0.5f;

@@ -113,11 +113,17 @@ __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive on the barrier at the same offset in CTA `cta_rank` of the cluster
+// arrive on the barrier at the same offset in CTA `cta_rank` of the cluster.  Default semantics (no cluster-scope
+// release: that costs a MEMBAR + L1 invalidate per arrival); the payload it publishes is either TMEM reads already
+// retired by tcgen05.wait::ld or shared-memory operand tiles already made visible by fence.proxy.async.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta_rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// arrive on the LEADER's (cluster rank 0) barrier from either CTA of a pair
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar, uint32_t my_rank) {
+    if (my_rank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0);
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;

@@ -122,12 +122,12 @@ class BatchedEstimator:
             self.lstm_variant = "fp32"
             if lstm_variant not in ("auto", "fp32", "tc"):
                 raise UserWarning(f"lstm_variant must be 'auto', 'fp32' or 'tc', got {lstm_variant!r}")
-            tc_ok = N.tc_supported(self.H, self.L)
+            tc_ok = N.tc_supported(self.I, self.H, self.L, self.O)
             if lstm_variant == "tc" and not tc_ok:
                 raise UserWarning(f"the tensor-core LSTM kernel does not support H={self.H}, L={self.L}")
             if lstm_variant == "tc" or (lstm_variant == "auto" and tc_ok and B * nF * self.n >= tc_min_rows):
                 self.tc_weights = torch.from_numpy(nn_models.pack_lstm_weights_tc(state)).to(dev)
-                assert self.tc_weights.numel() == N.tc_blob_bytes(self.H, self.L)
+                assert self.tc_weights.numel() == N.tc_blob_bytes(self.I, self.H, self.L)
                 ws_tc = N.workspace_bytes(self.I, self.H, self.L, self.T, self.O, B * nF, self.n, tensor_core=True) + 3 * 256 * self.T * self.H * 4
                 if ws_tc > self.workspace.numel():
                     self.workspace = torch.empty(ws_tc, dtype=torch.uint8, device=dev)

@@ -54,32 +54,36 @@ def pack_lstm_weights(state):
 def pack_lstm_weights_tc(state):
     """Reference state dict -> the fp16 blob of the tensor-core path (``csrc/ape_lstm_tc.cu``), as uint8 bytes.
 
-    Per layer l >= 1: for each CTA r of the pair, for each part (input weights, recurrent weights), for each chunk
-    c of 32 hidden units, the 64 gate columns  n = 64 r + nl  of the chunk's 128 (n = 4 * u_local + g, i.e. units
-    16 r .. 16 r + 15, gates i, f, g, o interleaved) as a K-major no-swizzle tile ``[H/8][64][8]`` halfs; then the
-    bias ``b_ih + b_hh`` in column order 4u + g, pre-multiplied by -log2(e) (i, f, o) or -2 log2(e) (g) so the
-    epilogue's sigmoid / tanh arguments come out of one FMA."""
+    Per layer: for each CTA r of the pair, for each chunk c of 32 hidden units, the 64 gate columns  n = 64 r + nl
+    of the chunk's 128 (n = 4 * u_local + g, i.e. units 16 r .. 16 r + 15 with gates i, f, g, o interleaved) as
+    K-major no-swizzle tiles ``[k-group][64][8]`` halfs - first the input weights (layer 0: K zero-padded to a
+    multiple of 16), then the recurrent weights; after both CTAs the bias ``b_ih + b_hh`` in column order 4u + g,
+    pre-multiplied by -log2(e) (i, f, o) or -2 log2(e) (g) so the epilogue's sigmoid / tanh arguments come out of
+    one FMA."""
     st = {k: np.asarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
           for k, v in state.items()}
     I, H, L, O = lstm_dims(st)
     log2e = np.float32(1.4426950408889634)
     parts = []
     nl = np.arange(64)
-    for l in range(1, L):
-        mats = (st[f"lstm.weight_ih_l{l}"], st[f"lstm.weight_hh_l{l}"])
+
+    def tile(w, rows, kpad):
+        t = np.zeros((64, kpad), np.float16)
+        t[:, : w.shape[1]] = w[rows].astype(np.float16)
+        return np.ascontiguousarray(t.reshape(64, kpad // 8, 8).transpose(1, 0, 2)).view(np.uint8).ravel()
+
+    for l in range(L):
+        w_ih, w_hh = st[f"lstm.weight_ih_l{l}"], st[f"lstm.weight_hh_l{l}"]
+        kin_pad = -(-w_ih.shape[1] // N.KSLICE) * N.KSLICE if l == 0 else H
         for r in range(2):
             n = 64 * r + nl
-            for w in mats:
-                for c in range(H // 32):
-                    rows = (n % 4) * H + 32 * c + n // 4
-                    tile = w[rows].astype(np.float16)                               # [64, H]
-                    parts.append(np.ascontiguousarray(tile.reshape(64, H // 8, 8).transpose(1, 0, 2)).view(np.uint8).ravel())
+            for c in range(H // 32):
+                rows = (n % 4) * H + 32 * c + n // 4
+                parts += [tile(w_ih, rows, kin_pad), tile(w_hh, rows, H)]
         bias = (st[f"lstm.bias_ih_l{l}"] + st[f"lstm.bias_hh_l{l}"]).reshape(4, H).T.copy()       # [u][g]
         bias *= -log2e
         bias[:, 2] *= np.float32(2.0)
         parts.append(np.ascontiguousarray(bias.reshape(-1), dtype=np.float32).view(np.uint8))
-    if not parts:
-        return np.zeros(0, np.uint8)
     return np.ascontiguousarray(np.concatenate(parts))
 
 

@@ -201,7 +201,7 @@ def run_ours(args, rank, world, local_rank):
     be = BatchedEstimator(kind=kind, layout=spec["layout"], state=state, seq_len=T, y_targets=spec["y_targets"],
                           stats=spec["stats"], n_streams=count, mc_samples=n, smooth=smooth, dropout=spec["p"],
                           frames_per_call=1, mask_mode=N.MASK_PHILOX, philox_seed=2026, first_stream=first,
-                          emit_samples=True)
+                          emit_samples=True, lstm_variant=args.lstm)
     K, W = args.steps, args.warmup
     # synthetic rows: 64 distinct seeded streams tiled over the shard (generation cost only), K+W frames
     base = syn.synth_rows(kind, min(64, count), K + W, config_id=3, first_stream=first)
@@ -224,12 +224,15 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- device-resident throughput ("value") ----
     be.reset()
-    for f in range(W):
-        be.step_device(frames_dev[f])
-    barrier()
-    launches0 = be.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
+        t_wait = time.time()
+        while not clk.lines and time.time() - t_wait < 10.0:  # nvidia-smi start-up must not land in the timed region
+            time.sleep(0.05)
+        for f in range(W):
+            be.step_device(frames_dev[f])
+        barrier()
+        launches0 = be.launches
         ev0.record()
         for f in range(W, W + K):
             be.step_device(frames_dev[f])
@@ -270,26 +273,34 @@ def run_ours(args, rank, world, local_rank):
     fp32_peak_tflops = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     total_est = count * K * world
+    tensor = be.lstm_variant == "tc"
+    if tensor:
+        roofline = {"bound": "tensor", "kernel": "lstm_layer_tc_kernel<128> (one layer >= 1 launch; tcgen05 cta_group::2, fp16 operands, fp32 accumulate)",
+                    "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst) [{peak_src}]; fp16 and bf16 tcgen05.mma run at the same rate"}
+    else:
+        roofline = {"bound": "fp32_ffma", "kernel": "lstm_layer_fma_kernel (one layer >= 1 launch)", "achieved": achieved,
+                    "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
+                    "peak_source": f"148 SM x 128 FFMA/clk x 2 x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz (nominal fp32 FMA peak at max SM clock; "
+                                   f"MEASURED_PEAKS.json [{peak_src}] has no fp32 figure)",
+                    "frac_of_bf16_tensor_peak": achieved / peaks["bf16_tflops"]}
+    roofline.update({"flops_per_launch": dom_flops, "ms_per_launch": dom_ms, "layer_ms": [float(v) for v in acc], "traffic": None})
 
     line = {
         "metric": METRIC, "value": total_est / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": ("f16 operands, f32 accumulate/state" if tensor else "f32"), "data": "synthetic",
         "config": {"workload": args.workload, "baseline_config": "watch+phone upper-arm estimator with quaternion FK, 1024 concurrent streams x 100 MC samples on 1 B200",
                    "model": {"I": I, "H": H, "L": L, "T": T, "O": O, "dropout": spec["p"]}, "streams_per_gpu": count,
                    "mc_samples": n, "smooth": smooth, "frames_per_step": 1, "estimates_per_step_per_gpu": count,
-                   "lstm_variant": "fp32_ffma", "rng": "philox4x32-10",
+                   "lstm_variant": ("tcgen05_fp16_operands_fp32_accumulate" if tensor else "fp32_ffma"),
+                   "tc_probe_error_m": be.tc_probe_error_m, "parity_tolerance_m": 1e-4, "rng": "philox4x32-10",
                    "l2": f"per-step working set (inter-layer sequences {rows_mc * T * H * 4 / 1e6:.0f} MB) exceeds the 126 MB L2"},
         "e2e": {"value": total_est / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": be.h2d_bytes_per_frame,
                 "d2h_bytes_per_step": be.d2h_bytes_per_frame, "ms_per_step": e2e_ms / K},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "fp32_ffma", "kernel": "lstm_layer_fma_kernel (one layer >= 1 launch)", "achieved": achieved,
-                     "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
-                     "peak_source": f"148 SM x 128 FFMA/clk x 2 x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz (nominal fp32 FMA peak at max SM clock; "
-                                    f"MEASURED_PEAKS.json [{peak_src}] has no fp32 figure)",
-                     "frac_of_bf16_tensor_peak": achieved / peaks["bf16_tflops"],
-                     "flops_per_launch": dom_flops, "ms_per_launch": dom_ms, "layer_ms": [float(v) for v in acc], "traffic": None},
+        "roofline": roofline,
         "checksum": checksum,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -317,6 +328,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=400, help="frames per worker of the bounded cpu_baseline sample")
     ap.add_argument("--ref-frames", type=int, default=100, help="--impl reference: frames per worker per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lstm", default="auto", choices=["auto", "fp32", "tc"], help="LSTM kernel variant (auto: probe-gated tensor cores)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -102,7 +102,7 @@ typedef struct ape_lstm_args {
                                   all_steps != 0: [E][n_samples][T][O] */
     int pred_ring;
     int all_steps;
-    /* tensor-core path only: fp16 gate weights of layers >= 1 packed by pack_lstm_weights_tc()
+    /* tensor-core path only: fp16 gate weights of all layers packed by pack_lstm_weights_tc()
        (ape_lstm_tc_blob_bytes() bytes, layout in csrc/ape_lstm_tc.cu); ignored by ape_mc_lstm_fma */
     const void* weights_tc;
     /* profiling: null, or L floats on the HOST - the call then brackets every layer launch with CUDA events,
@@ -114,12 +114,12 @@ int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_
 /* fp32 FFMA variant (parity anchor; H in {32, 64, 128, 256}). */
 int ape_mc_lstm_fma(const ape_lstm_args* args, void* stream);
 /*
- * Tensor-core variant (tcgen05, cta_group::2, TMEM accumulators): layer 0 in fp32, layers >= 1 with fp16 operands
- * and fp32 accumulation.  H in {64, 128}, L >= 2; same arguments and outputs as ape_mc_lstm_fma plus weights_tc.
+ * Tensor-core variant (tcgen05, cta_group::2, TMEM accumulators): fp16 operands, fp32 accumulation and cell state.
+ * H in {64, 128}, L >= 2, all_steps == 0; same arguments and outputs as ape_mc_lstm_fma plus weights_tc.
  * Use when the streams x MC-samples batch is large (>= a few thousand rows); the fp32 variant is the exact path.
  */
-int ape_mc_lstm_tc_supported(int H);
-int ape_lstm_tc_blob_bytes(int H, int L, int64_t* bytes);
+int ape_mc_lstm_tc_supported(int I, int H, int L, int O);
+int ape_lstm_tc_blob_bytes(int I, int H, int L, int64_t* bytes);
 int ape_mc_lstm_tc_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
 int ape_mc_lstm_tc(const ape_lstm_args* args, void* stream);
 /*
