@@ -232,30 +232,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
             const int e = valid ? row / a.n : 0, smp = valid ? row - e * a.n : 0;
             const int b = e / a.nF, f = a.frame0 + e % a.nF;
             for (int t = 0; t < T; ++t) {
-                if (!first) { mbar_wait(&bars[BAR_X_DONE], ph_xdone); ph_xdone ^= 1; }   // the previous x tile has been consumed
-                first = false;
                 if (a.in_mode == IN_UNITS || a.in_mode == IN_SHARED_UNITS) {
+                    // all loads of the step go out before anything waits; masks are ANDed in as the data lands; only the
+                    // shared-memory stores sit behind "the previous x tile has been consumed"
                     const uint4* src = reinterpret_cast<const uint4*>(a.in);
                     if (a.in_mode == IN_UNITS) src += ((((size_t)tile * T + t) * 2 + rank) * KG) * ROWS + row_l;
                     else src += ((((size_t)(e >> 8) * T + t) * 2 + ((e >> 7) & 1)) * KG) * ROWS + (e & 127);
-#pragma unroll 4
+                    uint4 pre[KG];
+#pragma unroll
+                    for (int j = 0; j < KG; ++j) pre[j] = valid ? __ldg(src + (size_t)j * ROWS) : make_uint4(0, 0, 0, 0);
+#pragma unroll
                     for (int j = 0; j < KG; ++j) {
-                        uint4 u4 = valid ? __ldg(src + (size_t)j * ROWS) : make_uint4(0, 0, 0, 0);
                         if (a.mask_mode == APE_MASK_PHILOX) {
                             const uint4 m = philox_keep_halfmask(a.seed, a.stream_id0 + (uint32_t)b, (uint32_t)f, (uint32_t)smp,
                                                                  (uint32_t)a.gap, (uint32_t)t, (uint32_t)j, a.keep_thr16);
-                            u4.x &= m.x; u4.y &= m.y; u4.z &= m.z; u4.w &= m.w;
+                            pre[j].x &= m.x; pre[j].y &= m.y; pre[j].z &= m.z; pre[j].w &= m.w;
                         } else if (a.mask_mode == APE_MASK_INJECTED && valid) {
                             const uint2 m = __ldg(reinterpret_cast<const uint2*>(
                                 a.masks + ((((size_t)e * a.n_gaps + a.gap) * T + t) * a.n + smp) * H + j * 8));
-                            u4.x &= ((m.x & 0xFFu) ? 0xFFFFu : 0u) | ((m.x & 0xFF00u) ? 0xFFFF0000u : 0u);
-                            u4.y &= ((m.x & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.x & 0xFF000000u) ? 0xFFFF0000u : 0u);
-                            u4.z &= ((m.y & 0xFFu) ? 0xFFFFu : 0u) | ((m.y & 0xFF00u) ? 0xFFFF0000u : 0u);
-                            u4.w &= ((m.y & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.y & 0xFF000000u) ? 0xFFFF0000u : 0u);
+                            pre[j].x &= ((m.x & 0xFFu) ? 0xFFFFu : 0u) | ((m.x & 0xFF00u) ? 0xFFFF0000u : 0u);
+                            pre[j].y &= ((m.x & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.x & 0xFF000000u) ? 0xFFFF0000u : 0u);
+                            pre[j].z &= ((m.y & 0xFFu) ? 0xFFFFu : 0u) | ((m.y & 0xFF00u) ? 0xFFFF0000u : 0u);
+                            pre[j].w &= ((m.y & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.y & 0xFF000000u) ? 0xFFFF0000u : 0u);
                         }
-                        *reinterpret_cast<uint4*>(sAx + unit_offset(ROWS, row_l, j)) = u4;
                     }
+                    if (!first) { mbar_wait(&bars[BAR_X_DONE], ph_xdone); ph_xdone ^= 1; }
+                    first = false;
+#pragma unroll
+                    for (int j = 0; j < KG; ++j) *reinterpret_cast<uint4*>(sAx + unit_offset(ROWS, row_l, j)) = pre[j];
                 } else {                                       // layer 0: fp32 features (window of the ring, or dense rows)
+                    if (!first) { mbar_wait(&bars[BAR_X_DONE], ph_xdone); ph_xdone ^= 1; }
+                    first = false;
                     const float* src = nullptr;
                     if (valid) {
                         if (a.in_mode == IN_DENSE_F32) {
@@ -279,10 +286,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 if (lane == 0) mbar_arrive_leader(&bars[BAR_X_READY], rank);
             }
         }
-    } else if (rank == 0 && lane == 0) {
-        // =================================== MMA issuer (leader CTA, one thread) =====================================
+    } else if (rank == 0) {
+        // =================================== MMA issuer (leader CTA; the whole warp runs, one elected lane issues) ======
         const uint32_t idesc = make_idesc_f16(256, 128);
-        const uint32_t aX = smem_u32(sAx), aH = smem_u32(sAh), wB = smem_u32(sW);
+        const uint64_t dX = make_desc(smem_u32(sAx), LBO_A, SBO), dH0 = make_desc(smem_u32(sAh), LBO_A, SBO);
+        const uint64_t dW = make_desc(smem_u32(sW), LBO_B, SBO);
         uint32_t ph_xready = 0, ph_hready = 0, ph_slot = 0;
         bool first = true;
         for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
@@ -293,29 +301,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     if (!first) { mbar_wait(&bars[BAR_SLOT_FREE + c], ph_slot); fence_after_sync(); }
-                    const uint32_t wb = wB + c * chunk_bytes;
-                    for (int k2 = 0; k2 < kgx / 2; ++k2)
-                        mma_f16<2>(tmem + c * 128, make_desc(aX + k2 * 2 * LBO_A, LBO_A, SBO), make_desc(wb + k2 * 2 * LBO_B, LBO_B, SBO),
-                                   idesc, k2 > 0 ? 1u : 0u);
-                    if (t == 0) commit_pair(&bars[BAR_ACC_READY + c], 0x3);      // h_{-1} = 0: no recurrent half
+                    if (elect_one()) {
+                        const uint64_t wb = desc_advance(dW, c * chunk_bytes);
+                        for (int k2 = 0; k2 < kgx / 2; ++k2)
+                            mma_f16<2>(tmem + c * 128, desc_advance(dX, k2 * 2 * LBO_A), desc_advance(wb, k2 * 2 * LBO_B), idesc, k2 > 0 ? 1u : 0u);
+                        if (t == 0) commit_pair(&bars[BAR_ACC_READY + c], 0x3);  // h_{-1} = 0: no recurrent half
+                    }
+                    __syncwarp();
                 }
                 if (!first) ph_slot ^= 1;
                 first = false;
-                commit_pair(&bars[BAR_X_DONE], 0x3);
+                if (elect_one()) commit_pair(&bars[BAR_X_DONE], 0x3);
+                __syncwarp();
                 if (t > 0) {
                     mbar_wait(&bars[BAR_H_READY], ph_hready);
                     ph_hready ^= 1;
                     fence_after_sync();
-                    const uint32_t ah = aH + (t & 1) * A_BYTES;
+                    if (elect_one()) {
+                        const uint64_t dH = desc_advance(dH0, (t & 1) * A_BYTES);
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        const uint32_t wb = wB + c * chunk_bytes + (uint32_t)kgx * KG_BYTES_B;
+                        for (int c = 0; c < NCH; ++c) {
+                            const uint64_t wb = desc_advance(dW, c * chunk_bytes + (uint32_t)kgx * KG_BYTES_B);
 #pragma unroll
-                        for (int k2 = 0; k2 < KG / 2; ++k2)
-                            mma_f16<2>(tmem + c * 128, make_desc(ah + k2 * 2 * LBO_A, LBO_A, SBO), make_desc(wb + k2 * 2 * LBO_B, LBO_B, SBO),
-                                       idesc, 1u);
-                        commit_pair(&bars[BAR_ACC_READY + c], 0x3);
+                            for (int k2 = 0; k2 < KG / 2; ++k2)
+                                mma_f16<2>(tmem + c * 128, desc_advance(dH, k2 * 2 * LBO_A), desc_advance(wb, k2 * 2 * LBO_B), idesc, 1u);
+                            commit_pair(&bars[BAR_ACC_READY + c], 0x3);
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }

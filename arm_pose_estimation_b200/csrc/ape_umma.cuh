@@ -57,6 +57,17 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy shared-memory writes (st.shared) -> visible to the async proxy the tensor core reads through
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a fully converged warp (the rest of the warp keeps executing the surrounding, warp-uniform code: that
+// lets the compiler keep descriptors in uniform registers instead of broadcasting them per instruction)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// descriptor with the start address advanced by `bytes` (no carry out of the 14-bit field for < 256 KB of smem)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+
 // ---- MMA issue (ONE thread): D[tmem] (+)= A[smem] * B[smem]^T -----------------------------------------------
 template <int CTA_GROUP>
 __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
