@@ -50,6 +50,8 @@ class LstmArgs(C.Structure):
         ("all_steps", C.c_int),
         ("weights_tc", C.c_void_p),
         ("layer_ms", C.c_void_p),
+        ("trace", C.c_void_p),
+        ("trace_layer", C.c_int),
     ]
 
 

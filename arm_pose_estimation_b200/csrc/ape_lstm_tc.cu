@@ -28,21 +28,23 @@
 namespace ape {
 namespace tc {
 
-constexpr int EPI_WARPS = 16, LOAD_WARPS = 4;
+constexpr int EPI_WARPS = 16, LOAD_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS;
-constexpr int THREADS = (MMA_WARP + 1) * 32;       // 16 epilogue + 4 operand-loader + 1 MMA-issue warps = 672
+constexpr int THREADS = (MMA_WARP + 1) * 32;       // 16 epilogue + 8 operand-loader + 1 MMA-issue warps = 800
 constexpr int ROWS = 128;                          // rows per CTA = TMEM lanes
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float EX2_CLAMP = 40.0f;                 // (1 + 2^40)^3 still fits fp32
 
 enum { IN_WINDOW_F32 = 0, IN_DENSE_F32 = 1, IN_SHARED_UNITS = 2, IN_UNITS = 3 };
-enum { BAR_X_READY = 0, BAR_X_DONE = 1, BAR_H_READY = 2, BAR_ACC_READY = 3, BAR_SLOT_FREE = 7, BAR_COUNT = 11 };
+enum { BAR_X_READY = 0, BAR_X_DONE = 1, BAR_ACC_READY = 2, BAR_SLOT_FREE = 6, BAR_H_READY = 10, BAR_COUNT = 14 };
 
 struct TcLayerArgs {
     const uint8_t* W;          // this layer: [cta 2][chunk][x k-groups then h k-groups][64 gate columns][8 halfs]
     const float* bias_s;       // [4H] column c = 4u+g, pre-multiplied by -log2(e) (i, f, o) / -2 log2(e) (g)
     int T, kgx, Kin;           // x-part: kgx k-groups (layer 0: ceil16(I)/8, else H/8) of which Kin columns are real
+    int rpc;                   // rows per CTA actually used (128, or 32 to spread a small layer 0 over more SMs)
+    int in_rpc_shift;          // IN_SHARED_UNITS: log2(rpc) of the producing layer
     int in_mode;
     const void* in;
     int feat_ring, nF, frame0, rows, n;
@@ -60,10 +62,19 @@ struct TcLayerArgs {
     float* preds;
     int pred_ring, n_out;
     int n_pair_tiles;
+    long long* trace;          // debugging: null, or [3 roles][16 steps][16 events] SM-clock stamps of the first tile of CTA 0
 };
 
+#ifndef APE_EXP
+#define APE_EXP 0            // timing experiments only (tools/tc_experiments.sh); 0 = the real kernel
+#endif
+#if APE_EXP == 2
+__device__ __forceinline__ float ex2_approx(float x) { return x * 0.99f; }
+__device__ __forceinline__ float rcp_approx(float x) { return x * 1.01f; }
+#else
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
 
 // One LSTM cell from the four ex2 ARGUMENTS  p = -(gate + bias) * log2e  (g gate: * 2 log2e):
 //   i*g~ = (1 - e_g) / ((1 + e_i)(1 + e_g)),  f = 1 / (1 + e_f)  share one reciprocal; h = o * tanh(c) another.
@@ -76,6 +87,10 @@ __device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po
     const float ec = ex2_approx(fminf(c * (-2.0f * LOG2E), EX2_CLAMP));
     h = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
 }
+
+// role 0 = epilogue warp 0 (chunk 0), role 1 = loader warp 16, role 2 = MMA issuer; only block 0, first tile, lane 0
+#define APE_TRACE(role, t, ev) do { if (a.trace && blockIdx.x == 0 && tile == cluster_id && lane == 0 && (t) < 16) \
+    a.trace[((role) * 16 + (t)) * 16 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
@@ -118,10 +133,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
     if (tid == 0) {
         mbar_init(&bars[BAR_X_READY], 2 * LOAD_WARPS);
         mbar_init(&bars[BAR_X_DONE], 1);
-        mbar_init(&bars[BAR_H_READY], 2 * EPI_WARPS);
         for (int c = 0; c < 4; ++c) {
             mbar_init(&bars[BAR_ACC_READY + c], 1);
             mbar_init(&bars[BAR_SLOT_FREE + c], 2 * EPI_WARPS);
+            mbar_init(&bars[BAR_H_READY + c], 2 * EPI_WARPS);   // the 32 hidden units of chunk c of h_t are in both CTAs' tiles
         }
         mbar_init_fence();
     }
@@ -133,15 +148,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 
     if (warp < EPI_WARPS) {
         // =================================== epilogue warps ===========================================================
-        const int q = warp & 3, s = warp >> 2;                 // TMEM lane quarter; 8-unit slice of every 32-unit chunk
+        // warp (q, s): rows 32q..32q+31 (its TMEM lane quarter) x the 8 hidden units 8s..8s+7 of EVERY 32-unit chunk.  Chunk c
+        // of the accumulator is drained by all warps at the start of pass c, so the issuer can refill it (x-part of the next
+        // step, then the recurrent pieces whose K-slices are already published) while passes c+1.. are still computing.
+        const int q = warp & 3, s = warp >> 2;
         const int row_l = 32 * q + lane;                       // local row == TMEM lane
         const uint32_t t_lane = (uint32_t)(32 * q) << 16;
+        const bool warp_live = 32 * q < a.rpc;                 // a quarter without rows only keeps the barrier protocol going
         uint32_t ph_acc = 0;
         float cst[NCH][8];
 
         for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
-            const int row = (tile * 2 + (int)rank) * ROWS + row_l;
-            const bool valid = row < a.rows;
+            const int row = (tile * 2 + (int)rank) * a.rpc + row_l;
+            const bool valid = row_l < a.rpc && row < a.rows;
 #pragma unroll
             for (int c = 0; c < NCH; ++c)
 #pragma unroll
@@ -153,31 +172,66 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 // last step of the last layer: h_T feeds the output layer only - keep it in fp32, [unit][row], in the two
                 // h tiles (units < H/2 in the tile being written, the rest in the tile the last MMAs have finished reading)
                 const bool final_f32 = a.preds != nullptr && t == T - 1;
+                if (warp == 0) APE_TRACE(0, t, 0);
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     mbar_wait(&bars[BAR_ACC_READY + c], ph_acc);
                     fence_after_sync();
+                    if (warp == 0) APE_TRACE(0, t, 1 + 3 * c);
+                    if (!warp_live) {
+                        if (lane == 0) {
+                            mbar_arrive_leader(&bars[BAR_SLOT_FREE + c], rank);
+                            if (t + 1 < T) mbar_arrive_leader(&bars[BAR_H_READY + c], rank);
+                        }
+                        continue;
+                    }
                     uint32_t r[32];
                     tmem_ld_x32(tmem + t_lane + (uint32_t)(c * 128 + 32 * s), r);
                     tmem_ld_wait();
                     fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(&bars[BAR_SLOT_FREE + c], rank);
+                    if (warp == 0) APE_TRACE(0, t, 2 + 3 * c);
 
                     const float4* bias4 = reinterpret_cast<const float4*>(sBias + (c * 32 + 8 * s) * 4);
-                    float hv[8];
+                    // The 8 cells advance in lock-step through the five transcendental stages, so every stage issues 8..32
+                    // INDEPENDENT MUFU ops back to back instead of one dependent chain per cell:
+                    //   e = 2^-(gate+bias)  ->  i*g~ and f share one reciprocal  ->  2^(-2c)  ->  h = o * tanh(c)
+                    float ev[32], hv[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
+#if APE_EXP == 5
+                        const float4 bs = make_float4(0.1f, 0.2f, 0.3f, 0.4f);
+#else
                         const float4 bs = bias4[u];
-                        const float pi = fmaf(__uint_as_float(r[4 * u + 0]), -LOG2E, bs.x);
-                        const float pf = fmaf(__uint_as_float(r[4 * u + 1]), -LOG2E, bs.y);
-                        const float pg = fmaf(__uint_as_float(r[4 * u + 2]), -2.0f * LOG2E, bs.z);
-                        const float po = fmaf(__uint_as_float(r[4 * u + 3]), -LOG2E, bs.w);
-                        lstm_cell(pi, pf, pg, po, cst[c][u], hv[u]);
+#endif
+                        ev[4 * u + 0] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 0]), -LOG2E, bs.x), EX2_CLAMP));
+                        ev[4 * u + 1] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 1]), -LOG2E, bs.y), EX2_CLAMP));
+                        ev[4 * u + 2] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 2]), -2.0f * LOG2E, bs.z), EX2_CLAMP));
+                        ev[4 * u + 3] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 3]), -LOG2E, bs.w), EX2_CLAMP));
                     }
+                    float num[8], den[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float ab = (1.0f + ev[4 * u + 0]) * (1.0f + ev[4 * u + 2]), cf = 1.0f + ev[4 * u + 1];
+                        num[u] = fmaf(cst[c][u], ab, (1.0f - ev[4 * u + 2]) * cf);
+                        den[u] = ab * cf;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) den[u] = rcp_approx(den[u]);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        cst[c][u] = num[u] * den[u];
+                        num[u] = ex2_approx(fminf(cst[c][u] * (-2.0f * LOG2E), EX2_CLAMP));              // e_c
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) den[u] = rcp_approx((1.0f + ev[4 * u + 3]) * (1.0f + num[u]));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) hv[u] = (1.0f - num[u]) * den[u];
+
                     const int j = 4 * c + s;                   // k-group of units 32c + 8s .. + 7
                     if (final_f32) {
-                        if (c >= NCH / 2 && c < NCH - 1) mbar_wait(&bars[BAR_ACC_READY + NCH - 1], ph_acc);   // all MMAs of the step retired
+                        if (c >= NCH / 2 && c < NCH - 1) mbar_wait(&bars[BAR_ACC_READY + NCH - 1], ph_acc);   // every MMA of the step retired
                         float* dst = reinterpret_cast<float*>(c < NCH / 2 ? sAh_next : sAh_prev) + ((8 * j) % (H / 2)) * ROWS + row_l;
 #pragma unroll
                         for (int u = 0; u < 8; ++u) dst[u * ROWS] = hv[u];
@@ -185,7 +239,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         *reinterpret_cast<uint4*>(sAh_next + unit_offset(ROWS, row_l, j)) =
                             make_uint4(pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]), pack_half2(hv[4], hv[5]), pack_half2(hv[6], hv[7]));
                     }
-                    if (a.out_units) {
+                    if (t + 1 < T) {                           // publish this chunk's slice of h_t: its K-slice of the next
+                        fence_proxy_async_smem();              // recurrent product can be issued while later chunks still run
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&bars[BAR_H_READY + c], rank);
+                    }
+                    if (warp == 0) APE_TRACE(0, t, 3 + 3 * c);
+                    if (a.out_units && APE_EXP != 4) {
                         const float os = a.out_scale;
                         a.out_units[((((size_t)tile * T + t) * 2 + rank) * KG + j) * ROWS + row_l] =
                             make_uint4(pack_half2(hv[0] * os, hv[1] * os), pack_half2(hv[2] * os, hv[3] * os),
@@ -193,11 +253,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     }
                 }
                 ph_acc ^= 1;
-                if (t + 1 < T) {
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&bars[BAR_H_READY], rank);
-                }
                 if (final_f32) {                               // output_layer (nn_models.py:189), last step only
                     epi_bar_sync();
                     if (valid) {
@@ -223,12 +278,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
         }
     } else if (warp < MMA_WARP) {
         // =================================== operand-loader warps: x_t -> sAx ===========================================
-        const int row_l = tid - EPI_THREADS;                   // one thread per row, all x k-groups
+        const int row_l = (tid - EPI_THREADS) & (ROWS - 1);    // two threads per row, each half of the x k-groups
+        const int half = (tid - EPI_THREADS) >> 7;
         uint32_t ph_xdone = 0;
         bool first = true;
         for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
-            const int row = (tile * 2 + (int)rank) * ROWS + row_l;
-            const bool valid = row < a.rows;
+            const int row = (tile * 2 + (int)rank) * a.rpc + row_l;
+            const bool valid = row_l < a.rpc && row < a.rows;
             const int e = valid ? row / a.n : 0, smp = valid ? row - e * a.n : 0;
             const int b = e / a.nF, f = a.frame0 + e % a.nF;
             for (int t = 0; t < T; ++t) {
@@ -237,29 +293,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     // shared-memory stores sit behind "the previous x tile has been consumed"
                     const uint4* src = reinterpret_cast<const uint4*>(a.in);
                     if (a.in_mode == IN_UNITS) src += ((((size_t)tile * T + t) * 2 + rank) * KG) * ROWS + row_l;
-                    else src += ((((size_t)(e >> 8) * T + t) * 2 + ((e >> 7) & 1)) * KG) * ROWS + (e & 127);
-                    uint4 pre[KG];
+                    else src += ((((size_t)(e >> (a.in_rpc_shift + 1)) * T + t) * 2 + ((e >> a.in_rpc_shift) & 1)) * KG) * ROWS +
+                                (e & ((1 << a.in_rpc_shift) - 1));
+                    if (warp == EPI_WARPS) APE_TRACE(1, t, 0);
+                    constexpr int KH = KG / 2;
+                    const int j0 = half * KH;
+                    src += (size_t)j0 * ROWS;
+                    uint4 pre[KH];
 #pragma unroll
-                    for (int j = 0; j < KG; ++j) pre[j] = valid ? __ldg(src + (size_t)j * ROWS) : make_uint4(0, 0, 0, 0);
+                    for (int jj = 0; jj < KH; ++jj) pre[jj] = valid ? __ldg(src + (size_t)jj * ROWS) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                    for (int j = 0; j < KG; ++j) {
-                        if (a.mask_mode == APE_MASK_PHILOX) {
+                    for (int jj = 0; jj < KH; ++jj) {
+                        const int j = j0 + jj;
+                        if (a.mask_mode == APE_MASK_PHILOX && APE_EXP != 3) {
                             const uint4 m = philox_keep_halfmask(a.seed, a.stream_id0 + (uint32_t)b, (uint32_t)f, (uint32_t)smp,
                                                                  (uint32_t)a.gap, (uint32_t)t, (uint32_t)j, a.keep_thr16);
-                            pre[j].x &= m.x; pre[j].y &= m.y; pre[j].z &= m.z; pre[j].w &= m.w;
+                            pre[jj].x &= m.x; pre[jj].y &= m.y; pre[jj].z &= m.z; pre[jj].w &= m.w;
                         } else if (a.mask_mode == APE_MASK_INJECTED && valid) {
                             const uint2 m = __ldg(reinterpret_cast<const uint2*>(
                                 a.masks + ((((size_t)e * a.n_gaps + a.gap) * T + t) * a.n + smp) * H + j * 8));
-                            pre[j].x &= ((m.x & 0xFFu) ? 0xFFFFu : 0u) | ((m.x & 0xFF00u) ? 0xFFFF0000u : 0u);
-                            pre[j].y &= ((m.x & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.x & 0xFF000000u) ? 0xFFFF0000u : 0u);
-                            pre[j].z &= ((m.y & 0xFFu) ? 0xFFFFu : 0u) | ((m.y & 0xFF00u) ? 0xFFFF0000u : 0u);
-                            pre[j].w &= ((m.y & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.y & 0xFF000000u) ? 0xFFFF0000u : 0u);
+                            pre[jj].x &= ((m.x & 0xFFu) ? 0xFFFFu : 0u) | ((m.x & 0xFF00u) ? 0xFFFF0000u : 0u);
+                            pre[jj].y &= ((m.x & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.x & 0xFF000000u) ? 0xFFFF0000u : 0u);
+                            pre[jj].z &= ((m.y & 0xFFu) ? 0xFFFFu : 0u) | ((m.y & 0xFF00u) ? 0xFFFF0000u : 0u);
+                            pre[jj].w &= ((m.y & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.y & 0xFF000000u) ? 0xFFFF0000u : 0u);
                         }
                     }
+                    if (warp == EPI_WARPS) APE_TRACE(1, t, 1);
                     if (!first) { mbar_wait(&bars[BAR_X_DONE], ph_xdone); ph_xdone ^= 1; }
                     first = false;
+                    if (warp == EPI_WARPS) APE_TRACE(1, t, 2);
 #pragma unroll
-                    for (int j = 0; j < KG; ++j) *reinterpret_cast<uint4*>(sAx + unit_offset(ROWS, row_l, j)) = pre[j];
+                    for (int jj = 0; jj < KH; ++jj) *reinterpret_cast<uint4*>(sAx + unit_offset(ROWS, row_l, j0 + jj)) = pre[jj];
                 } else {                                       // layer 0: fp32 features (window of the ring, or dense rows)
                     if (!first) { mbar_wait(&bars[BAR_X_DONE], ph_xdone); ph_xdone ^= 1; }
                     first = false;
@@ -273,7 +337,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                             src = reinterpret_cast<const float*>(a.in) + ((size_t)b * a.feat_ring + fw % a.feat_ring) * a.Kin;
                         }
                     }
-                    for (int j = 0; j < kgx; ++j) {
+                    for (int j = half; j < kgx; j += 2) {
                         float v[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) v[k] = (valid && 8 * j + k < a.Kin) ? __ldg(src + 8 * j + k) : 0.0f;
@@ -284,6 +348,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&bars[BAR_X_READY], rank);
+                if (warp == EPI_WARPS) APE_TRACE(1, t, 3);
             }
         }
     } else if (rank == 0) {
@@ -291,45 +356,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
         const uint32_t idesc = make_idesc_f16(256, 128);
         const uint64_t dX = make_desc(smem_u32(sAx), LBO_A, SBO), dH0 = make_desc(smem_u32(sAh), LBO_A, SBO);
         const uint64_t dW = make_desc(smem_u32(sW), LBO_B, SBO);
+        // Issue order inside a step follows the order in which the epilogue of the PREVIOUS step releases things:
+        //   SLOT_FREE[c]  (chunk c of the accumulator drained)      -> x-part of chunk c, then its recurrent pieces for the
+        //                                                              K-slices already published
+        //   H_READY[c']   (units 32c'..32c'+31 of h_{t-1} published) -> recurrent pieces (c, c') of every chunk c <= c'
+        // so when the last slice arrives only 2 MMAs stand between it and ACC_READY[0].
         uint32_t ph_xready = 0, ph_hready = 0, ph_slot = 0;
         bool first = true;
+        constexpr int KS2 = 2;                                  // K=16 MMAs per 32-unit K-slice (4 k-groups)
         for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
             for (int t = 0; t < T; ++t) {
+                APE_TRACE(2, t, 0);
                 mbar_wait(&bars[BAR_X_READY], ph_xready);
                 ph_xready ^= 1;
                 fence_after_sync();
+                APE_TRACE(2, t, 1);
+                const uint64_t dH = desc_advance(dH0, (t & 1) * A_BYTES);
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     if (!first) { mbar_wait(&bars[BAR_SLOT_FREE + c], ph_slot); fence_after_sync(); }
+                    APE_TRACE(2, t, 2 + 3 * c);
                     if (elect_one()) {
-                        const uint64_t wb = desc_advance(dW, c * chunk_bytes);
+                        const uint64_t wx = desc_advance(dW, c * chunk_bytes);
                         for (int k2 = 0; k2 < kgx / 2; ++k2)
-                            mma_f16<2>(tmem + c * 128, desc_advance(dX, k2 * 2 * LBO_A), desc_advance(wb, k2 * 2 * LBO_B), idesc, k2 > 0 ? 1u : 0u);
+                            mma_f16<2>(tmem + c * 128, desc_advance(dX, k2 * 2 * LBO_A), desc_advance(wx, k2 * 2 * LBO_B), idesc, k2 > 0 ? 1u : 0u);
                         if (t == 0) commit_pair(&bars[BAR_ACC_READY + c], 0x3);  // h_{-1} = 0: no recurrent half
-                    }
-                    __syncwarp();
-                }
-                if (!first) ph_slot ^= 1;
-                first = false;
-                if (elect_one()) commit_pair(&bars[BAR_X_DONE], 0x3);
-                __syncwarp();
-                if (t > 0) {
-                    mbar_wait(&bars[BAR_H_READY], ph_hready);
-                    ph_hready ^= 1;
-                    fence_after_sync();
-                    if (elect_one()) {
-                        const uint64_t dH = desc_advance(dH0, (t & 1) * A_BYTES);
+                        if (c == NCH - 1) commit_pair(&bars[BAR_X_DONE], 0x3);
+                        if (t > 0) {
+                            const uint64_t wh = desc_advance(wx, (uint32_t)kgx * KG_BYTES_B);
 #pragma unroll
-                        for (int c = 0; c < NCH; ++c) {
-                            const uint64_t wb = desc_advance(dW, c * chunk_bytes + (uint32_t)kgx * KG_BYTES_B);
+                            for (int cs = 0; cs < c; ++cs)                       // slices published before this chunk drained
 #pragma unroll
-                            for (int k2 = 0; k2 < KG / 2; ++k2)
-                                mma_f16<2>(tmem + c * 128, desc_advance(dH, k2 * 2 * LBO_A), desc_advance(wb, k2 * 2 * LBO_B), idesc, 1u);
-                            commit_pair(&bars[BAR_ACC_READY + c], 0x3);
+                                for (int k2 = cs * KS2; k2 < (cs + 1) * KS2; ++k2)
+                                    mma_f16<2>(tmem + c * 128, desc_advance(dH, k2 * 2 * LBO_A), desc_advance(wh, k2 * 2 * LBO_B), idesc, 1u);
                         }
                     }
                     __syncwarp();
+                    APE_TRACE(2, t, 3 + 3 * c);
+                    if (t > 0) {
+                        mbar_wait(&bars[BAR_H_READY + c], ph_hready);           // slice c of h_{t-1}
+                        fence_after_sync();
+                        APE_TRACE(2, t, 4 + 3 * c);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int cc = 0; cc <= c; ++cc) {                    // chunks whose x-part is already in flight
+                                const uint64_t wh = desc_advance(dW, cc * chunk_bytes + (uint32_t)kgx * KG_BYTES_B);
+#pragma unroll
+                                for (int k2 = c * KS2; k2 < (c + 1) * KS2; ++k2)
+                                    mma_f16<2>(tmem + cc * 128, desc_advance(dH, k2 * 2 * LBO_A), desc_advance(wh, k2 * 2 * LBO_B), idesc, 1u);
+                                if (c == NCH - 1) commit_pair(&bars[BAR_ACC_READY + cc], 0x3);
+                            }
+                        }
+                        __syncwarp();
+                    }
                 }
+                APE_TRACE(2, t, 14);
+                if (!first) ph_slot ^= 1;
+                if (t > 0) ph_hready ^= 1;
+                first = false;
             }
         }
     }
@@ -355,6 +439,8 @@ template <int H> static int launch(const TcLayerArgs& a, int sm_count, cudaStrea
 }  // namespace tc
 }  // namespace ape
 
+// rows per CTA of layer 0 (one row per estimate): a small batch is spread over more CTA pairs, 32 rows each
+static int tc_rpc0(long long E) { return E >= 16384 ? 128 : 32; }
 static int tc_kgx(int layer, int I, int H) { return layer == 0 ? ape_pack_kin_pad(0, I, H) / 8 : H / 8; }
 static size_t tc_layer_bytes(int layer, int I, int H) {
     return (size_t)2 * (H / 32) * (tc_kgx(layer, I, H) + H / 8) * 64 * 16 + (size_t)4 * H * 4;
@@ -376,7 +462,8 @@ extern "C" int ape_mc_lstm_tc_supported(int I, int H, int L, int O) {
 extern "C" int ape_mc_lstm_tc_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes) {
     if (!bytes || I < 1 || H < 1 || L < 1 || T < 1 || O < 1 || E < 0 || n_samples < 1) return APE_ERR_BAD_ARG;
     if (!ape_mc_lstm_tc_supported(I, H, L, O)) return APE_ERR_UNSUPPORTED;
-    const uint64_t tiles0 = ((uint64_t)E + 255) / 256, tiles1 = ((uint64_t)E * n_samples + 255) / 256;
+    const uint64_t rpc0 = tc_rpc0(E);
+    const uint64_t tiles0 = ((uint64_t)E + 2 * rpc0 - 1) / (2 * rpc0), tiles1 = ((uint64_t)E * n_samples + 255) / 256;
     const uint64_t u0 = (tiles0 * 256 * T * H * 2 + 255) & ~(uint64_t)255, u1 = (tiles1 * 256 * T * H * 2 + 255) & ~(uint64_t)255;
     *bytes = u0 + (L > 3 ? 2 : (L > 2 ? 1 : 0)) * u1 + 512;
     return APE_OK;
@@ -397,7 +484,8 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
     APE_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
 
     const long long rows = E * g->n_samples;
-    const int tiles0 = (int)((E + 255) / 256), tiles1 = (int)((rows + 255) / 256);
+    const int rpc0 = tc_rpc0(E);
+    const int tiles0 = (int)((E + 2 * rpc0 - 1) / (2 * rpc0)), tiles1 = (int)((rows + 255) / 256);
     const size_t u0 = ((size_t)tiles0 * 256 * g->T * g->H * 2 + 255) & ~(size_t)255;
     const size_t u1 = ((size_t)tiles1 * 256 * g->T * g->H * 2 + 255) & ~(size_t)255;
     char* wsp = (char*)(((uintptr_t)g->workspace + 255) & ~(uintptr_t)255);
@@ -426,6 +514,7 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
             a.in_mode = g->x_dense ? tc::IN_DENSE_F32 : tc::IN_WINDOW_F32;
             a.in = g->x_dense ? (const void*)g->x_dense : (const void*)g->feat_ring_buf;
             a.rows = (int)E; a.n = 1;
+            a.rpc = rpc0;
             a.n_pair_tiles = tiles0;
             a.mask_mode = APE_MASK_NONE;
             a.out_units = units0;
@@ -433,6 +522,8 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
             a.in_mode = l == 1 ? tc::IN_SHARED_UNITS : tc::IN_UNITS;
             a.in = l == 1 ? (const void*)units0 : (const void*)units[(l - 2) & 1];
             a.rows = (int)rows; a.n = g->n_samples;
+            a.rpc = 128;
+            a.in_rpc_shift = rpc0 == 128 ? 7 : 5;
             a.n_pair_tiles = tiles1;
             a.mask_mode = g->mask_mode;
             a.out_units = last ? nullptr : units[(l - 1) & 1];
@@ -446,6 +537,7 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
         a.O = g->O;
         a.preds = last ? g->preds : nullptr;
         a.pred_ring = g->pred_ring; a.n_out = g->n_samples;
+        a.trace = (g->trace && l == g->trace_layer) ? (long long*)g->trace : nullptr;
         rc = H == 128 ? tc::launch<128>(a, sm_count, st) : tc::launch<64>(a, sm_count, st);
         if (rc != APE_OK) return rc;
         if (prof) APE_CUDA_TRY(cudaEventRecord(ev[l + 1], st));

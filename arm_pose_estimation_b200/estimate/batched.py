@@ -40,6 +40,25 @@ def shard_streams(n_streams, world_size, rank):
     return first, count
 
 
+def gather_host_results(local, first_stream, n_streams, group=None):
+    """The only cross-rank step of a sharded job: rank 0 collects every rank's per-stream HOST results (a numpy array
+    whose axis 0 is this rank's streams) into one array ordered by global stream id; other ranks get ``None``.
+    Works on any ``torch.distributed`` backend (results are already on the host)."""
+    import torch.distributed as dist
+    local = np.ascontiguousarray(local)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object((int(first_stream), local), parts, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = np.empty((n_streams,) + local.shape[1:], dtype=local.dtype)
+    for first, arr in parts:
+        out[first:first + len(arr)] = arr
+    return out
+
+
 def ring_slots(n_frames_per_call, history):
     """Slots a device ring needs so that one call of ``n_frames_per_call`` frames still finds the ``history - 1``
     frames before its first one (``history`` = sequence_len for features, smooth for predictions)."""
@@ -58,6 +77,21 @@ class EstimateBatch:
     def host(self):
         f = lambda t: None if t is None else t.cpu().numpy()
         return EstimateBatch(f(self.msg), f(self.std), f(self.samples), f(self.status), self.frame0)
+
+
+class PendingEstimate:
+    """Handle of an enqueued ``BatchedEstimator.submit``: ``result()`` waits for its D2H copy and returns host arrays."""
+
+    def __init__(self, owner, slot, nF, frame0, event):
+        self.owner, self.slot, self.nF, self.frame0, self.event = owner, slot, nF, frame0, event
+
+    def done(self):
+        return self.event.query()
+
+    def result(self):
+        self.event.synchronize()
+        msg, std, samples, status = self.owner._host_views(self.slot, self.nF)
+        return EstimateBatch(msg, std, samples, status, self.frame0)
 
 
 class BatchedEstimator:
@@ -101,19 +135,23 @@ class BatchedEstimator:
             self.raw = torch.zeros((B, nF, self.ncols), dtype=f32, device=dev)
             self.feats = torch.zeros((B, self.feat_ring, self.I), dtype=f32, device=dev)
             self.preds = torch.zeros((B, self.pred_ring, self.n, self.O), dtype=f32, device=dev)
-            self.msg = torch.zeros((B, nF, 25), dtype=f32, device=dev)
-            self.std = torch.zeros((B, nF, 6), dtype=f32, device=dev)
-            self.samples = torch.zeros((B, nF, self.S, 6), dtype=f32, device=dev) if emit_samples else None
-            self.status = torch.zeros((B, nF), dtype=torch.int32, device=dev)
+            # results live in ONE device buffer [msg | std | status | samples] so a full call leaves in one D2H copy
+            E = B * nF
+            n_words = E * (25 + 6 + 1) + (E * self.S * 6 if emit_samples else 0)
+            # (two of them: the D2H copy of call k runs on a side stream under the kernels of call k+1)
+            self.out_bufs = [torch.zeros(n_words, dtype=f32, device=dev) for _ in range(2)]
+            self.copy_stream = torch.cuda.Stream(device=dev)
+            self.copy_done = [None, None]
+            self._use_out(0)
             # sized for the largest call; a shorter call re-tiles its rows, so leave one tile of slack per buffer
             ws_bytes = N.workspace_bytes(self.I, self.H, self.L, self.T, self.O, B * nF, self.n) + 3 * 64 * self.T * self.H * 4
             self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            # pinned staging for the host-facing calls
-            self.raw_host = torch.zeros((B, nF, self.ncols), dtype=f32).pin_memory()
-            self.msg_host = torch.zeros((B, nF, 25), dtype=f32).pin_memory()
-            self.std_host = torch.zeros((B, nF, 6), dtype=f32).pin_memory()
-            self.samples_host = torch.zeros((B, nF, self.S, 6), dtype=f32).pin_memory() if emit_samples else None
-            self.status_host = torch.zeros((B, nF), dtype=torch.int32).pin_memory()
+            # pinned staging for the host-facing calls: two slots, so call k+1 can be staged and enqueued while the
+            # results of call k are still on their way back (submit() / PendingEstimate.result())
+            self.raw_host = [torch.zeros((B, nF, self.ncols), dtype=f32).pin_memory() for _ in range(2)]
+            self.out_host = [torch.zeros(n_words, dtype=f32).pin_memory() for _ in range(2)]
+            self.slot_event = [None, None]
+            self.submits = 0
             # ---- which LSTM kernel: fp32 FFMA (exact) or tcgen05 fp16-operand tensor cores ----------------------
             # Tensor cores only when the streams x MC-samples batch is a real dense contraction AND the fp16-operand
             # result stays within tc_tolerance_m of the fp32 kernel on a probe batch of THIS model's weights.
@@ -171,12 +209,21 @@ class BatchedEstimator:
         torch.cuda.current_stream().synchronize()
         return float((outs[0] - outs[1]).abs().max().item())
 
+    def _use_out(self, k):
+        """Point the result views at device output buffer ``k``."""
+        B, nF, E = self.B, self.nF_max, self.B * self.nF_max
+        self.out_slot, self.out_all = k, self.out_bufs[k]
+        self.msg = self.out_all[: E * 25].view(B, nF, 25)
+        self.std = self.out_all[E * 25: E * 31].view(B, nF, 6)
+        self.status = self.out_all[E * 31: E * 32].view(torch.int32).view(B, nF)
+        self.samples = self.out_all[E * 32:].view(B, nF, self.S, 6) if self.emit_samples else None
+
     def reset(self):
         """Forget all history, like ``Estimator.reset`` (estimator.py:88-91): the next row is frame 0 again."""
         self.frame = 0
 
     # ---- device path -----------------------------------------------------------------------------------
-    def step_device(self, raw, n_frames=None, masks=None, layer_ms=None):
+    def step_device(self, raw, n_frames=None, masks=None, layer_ms=None, trace=None, trace_layer=1):
         """``raw``: device tensor ``[B, nF, ncols]`` float32 (nF <= frames_per_call).  Enqueues the three stages
         on the current stream and returns an ``EstimateBatch`` of views into the estimator's device buffers."""
         nF = int(raw.shape[1]) if n_frames is None else int(n_frames)
@@ -209,6 +256,8 @@ class BatchedEstimator:
         a.weights_tc = None if self.tc_weights is None else self.tc_weights.data_ptr()
         if layer_ms is not None:                     # profiling leg: float32 host array of L entries, filled on return
             a.layer_ms = layer_ms.ctypes.data
+        if trace is not None:                        # debugging: device int64[768] of SM-clock stamps (tensor-core path)
+            a.trace, a.trace_layer = trace.data_ptr(), trace_layer
         N.check(self._lstm_fn()(a, st), "ape_mc_lstm")
         N.check(lib.ape_fk_reduce(N.ptr(self.preds), self.pred_ring, N.ptr(self.yy_m), N.ptr(self.yy_s), N.ptr(self.body),
                                   self.target, self.O, B, nF, self.frame, self.n, self.smooth,
@@ -228,35 +277,60 @@ class BatchedEstimator:
         return buf.reshape(-1)[: self.B * nF * int(np.prod(tail, dtype=np.int64))].view(self.B, nF, *tail)
 
     # ---- host-facing path: pinned H2D, the three stages, pinned D2H ------------------------------------------
-    def step(self, rows, masks=None, sync=True):
-        """``rows``: host array ``[B, nF, ncols]`` (or ``[B, ncols]`` for one frame) of float32 wire rows.
-        Returns an ``EstimateBatch`` of HOST arrays (views of pinned buffers, valid until the next call)."""
+    def submit(self, rows, masks=None):
+        """Stage ``rows`` (host array ``[B, nF, ncols]`` or ``[B, ncols]`` of float32 wire rows) in pinned memory and
+        enqueue H2D copy -> the three stages -> D2H copy on the current stream WITHOUT waiting.  Returns a
+        ``PendingEstimate``; at most two may be outstanding (two staging slots)."""
         rows = np.asarray(rows, dtype=np.float32)
         if rows.ndim == 2:
             rows = rows[:, None, :]
         nF = rows.shape[1]
         if rows.shape[0] != self.B or nF > self.nF_max or rows.shape[2] != self.ncols:
             raise UserWarning(f"rows must be [B={self.B}, nF<={self.nF_max}, {self.ncols}], got {rows.shape}")
+        slot = self.submits % 2
+        self.submits += 1
+        if self.slot_event[slot] is not None:
+            self.slot_event[slot].synchronize()           # the slot's previous results have landed; its staging is free
         with torch.cuda.device(self.device):
-            if nF == self.nF_max:
-                self.raw_host.numpy()[...] = rows
-                self.raw.copy_(self.raw_host, non_blocking=True)
-                raw = self.raw
-            else:                                        # short call: a contiguous [B, nF, ncols] staging view
-                raw = torch.from_numpy(np.ascontiguousarray(rows)).to(self.device)
+            E = self.B * nF
+            stage = self.raw_host[slot].view(-1)[: E * self.ncols].view(self.B, nF, self.ncols)
+            stage.numpy()[...] = rows
+            raw = self.raw.view(-1)[: E * self.ncols].view(self.B, nF, self.ncols)
+            raw.copy_(stage, non_blocking=True)
+            main = torch.cuda.current_stream()
+            self._use_out(slot)
+            if self.copy_done[slot] is not None:
+                main.wait_event(self.copy_done[slot])     # device buffer `slot` has been read back (call k-2)
             out = self.step_device(raw, nF, masks)
-            host = []
-            for dev_t, host_buf in ((out.msg, self.msg_host), (out.std, self.std_host), (out.samples, self.samples_host),
-                                    (out.status, self.status_host)):
-                if dev_t is None:
-                    host.append(None)
-                    continue
-                hv = self._view(host_buf, nF)
-                hv.copy_(dev_t, non_blocking=True)
-                host.append(hv.numpy())
-            if sync:
-                torch.cuda.current_stream().synchronize()
-        return EstimateBatch(host[0], host[1], host[2], host[3], out.frame0)
+            computed = torch.cuda.Event()
+            computed.record(main)
+            host, dev_out = self.out_host[slot], self.out_all
+            self.copy_stream.wait_event(computed)
+            with torch.cuda.stream(self.copy_stream):
+                if nF == self.nF_max:
+                    host.copy_(dev_out, non_blocking=True)
+                else:                                    # short call: the kernels packed E estimates at the front of each part
+                    Em = self.B * self.nF_max
+                    for off, width in ((0, 25), (Em * 25, 6), (Em * 31, 1)) + (((Em * 32, self.S * 6),) if self.emit_samples else ()):
+                        host[off: off + E * width].copy_(dev_out[off: off + E * width], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            self.slot_event[slot] = ev
+            self.copy_done[slot] = ev
+        return PendingEstimate(self, slot, nF, out.frame0, ev)
+
+    def _host_views(self, slot, nF):
+        host, E, Em = self.out_host[slot].numpy(), self.B * nF, self.B * self.nF_max
+        msg = host[: E * 25].reshape(self.B, nF, 25)
+        std = host[Em * 25: Em * 25 + E * 6].reshape(self.B, nF, 6)
+        status = host[Em * 31: Em * 31 + E].view(np.int32).reshape(self.B, nF)
+        samples = host[Em * 32: Em * 32 + E * self.S * 6].reshape(self.B, nF, self.S, 6) if self.emit_samples else None
+        return msg, std, samples, status
+
+    def step(self, rows, masks=None):
+        """``submit`` + wait.  Returns an ``EstimateBatch`` of HOST arrays (views of a pinned staging slot, valid until
+        the slot is reused two calls later)."""
+        return self.submit(rows, masks).result()
 
     @property
     def h2d_bytes_per_frame(self):

@@ -108,6 +108,10 @@ typedef struct ape_lstm_args {
     /* profiling: null, or L floats on the HOST - the call then brackets every layer launch with CUDA events,
        synchronises the stream and writes each layer's device time in milliseconds (bench.py's roofline leg) */
     float* layer_ms;
+    /* debugging (tensor-core path): null, or a device buffer of 768 int64 that receives SM-clock stamps of the first
+       tile of CTA 0 of layer `trace_layer` ([role: epilogue, loader, issuer][step < 16][event < 16]) */
+    void* trace;
+    int trace_layer;
 } ape_lstm_args;
 
 int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
