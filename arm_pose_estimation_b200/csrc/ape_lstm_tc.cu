@@ -173,83 +173,99 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 // h tiles (units < H/2 in the tile being written, the rest in the tile the last MMAs have finished reading)
                 const bool final_f32 = a.preds != nullptr && t == T - 1;
                 if (warp == 0) APE_TRACE(0, t, 0);
+                if (!warp_live) {
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    mbar_wait(&bars[BAR_ACC_READY + c], ph_acc);
-                    fence_after_sync();
-                    if (warp == 0) APE_TRACE(0, t, 1 + 3 * c);
-                    if (!warp_live) {
+                    for (int c = 0; c < NCH; ++c) {
+                        mbar_wait(&bars[BAR_ACC_READY + c], ph_acc);
                         if (lane == 0) {
                             mbar_arrive_leader(&bars[BAR_SLOT_FREE + c], rank);
                             if (t + 1 < T) mbar_arrive_leader(&bars[BAR_H_READY + c], rank);
                         }
-                        continue;
                     }
-                    uint32_t r[32];
-                    tmem_ld_x32(tmem + t_lane + (uint32_t)(c * 128 + 32 * s), r);
-                    tmem_ld_wait();
-                    fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&bars[BAR_SLOT_FREE + c], rank);
-                    if (warp == 0) APE_TRACE(0, t, 2 + 3 * c);
-
-                    const float4* bias4 = reinterpret_cast<const float4*>(sBias + (c * 32 + 8 * s) * 4);
-                    // The 8 cells advance in lock-step through the five transcendental stages, so every stage issues 8..32
-                    // INDEPENDENT MUFU ops back to back instead of one dependent chain per cell:
-                    //   e = 2^-(gate+bias)  ->  i*g~ and f share one reciprocal  ->  2^(-2c)  ->  h = o * tanh(c)
-                    float ev[32], hv[8];
+                } else {
+                    // Half-passes of 4 hidden units (16 accumulator columns), double-buffered: the TMEM load of half-pass
+                    // hp+1 is in flight while the cells of half-pass hp are computed.
+                    uint32_t rbuf[2][16];
+                    float hlo[4];
+                    mbar_wait(&bars[BAR_ACC_READY + 0], ph_acc);
+                    fence_after_sync();
+                    tmem_ld_x16(tmem + t_lane + (uint32_t)(32 * s), rbuf[0]);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int hp = 0; hp < 2 * NCH; ++hp) {
+                        const int c = hp >> 1, half = hp & 1;
+                        uint32_t* r = rbuf[hp & 1];
+                        tmem_ld_wait();                        // this half-pass's columns have landed
+                        if (half == 1) {                       // chunk c fully drained: the issuer may refill it
+                            fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_leader(&bars[BAR_SLOT_FREE + c], rank);
+                            if (warp == 0) APE_TRACE(0, t, 2 + 3 * c);
+                        }
+                        if (hp + 1 < 2 * NCH) {
+                            if (half == 1) {
+                                mbar_wait(&bars[BAR_ACC_READY + c + 1], ph_acc);
+                                fence_after_sync();
+                                if (warp == 0) APE_TRACE(0, t, 1 + 3 * (c + 1));
+                            }
+                            tmem_ld_x16(tmem + t_lane + (uint32_t)(((hp + 1) >> 1) * 128 + 32 * s + 16 * ((hp + 1) & 1)), rbuf[(hp + 1) & 1]);
+                        }
+                        const float4* bias4 = reinterpret_cast<const float4*>(sBias + (c * 32 + 8 * s + 4 * half) * 4);
+                        // the 4 cells advance in lock-step through the transcendental stages (independent MUFU ops back to back):
+                        //   e = 2^-(gate+bias)  ->  i*g~ and f share one reciprocal  ->  2^(-2c)  ->  h = o * tanh(c)
+                        float ev[16], hv[4], num[4], den[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
 #if APE_EXP == 5
-                        const float4 bs = make_float4(0.1f, 0.2f, 0.3f, 0.4f);
+                            const float4 bs = make_float4(0.1f, 0.2f, 0.3f, 0.4f);
 #else
-                        const float4 bs = bias4[u];
+                            const float4 bs = bias4[u];
 #endif
-                        ev[4 * u + 0] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 0]), -LOG2E, bs.x), EX2_CLAMP));
-                        ev[4 * u + 1] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 1]), -LOG2E, bs.y), EX2_CLAMP));
-                        ev[4 * u + 2] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 2]), -2.0f * LOG2E, bs.z), EX2_CLAMP));
-                        ev[4 * u + 3] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 3]), -LOG2E, bs.w), EX2_CLAMP));
-                    }
-                    float num[8], den[8];
+                            ev[4 * u + 0] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 0]), -LOG2E, bs.x), EX2_CLAMP));
+                            ev[4 * u + 1] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 1]), -LOG2E, bs.y), EX2_CLAMP));
+                            ev[4 * u + 2] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 2]), -2.0f * LOG2E, bs.z), EX2_CLAMP));
+                            ev[4 * u + 3] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 3]), -LOG2E, bs.w), EX2_CLAMP));
+                        }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float ab = (1.0f + ev[4 * u + 0]) * (1.0f + ev[4 * u + 2]), cf = 1.0f + ev[4 * u + 1];
-                        num[u] = fmaf(cst[c][u], ab, (1.0f - ev[4 * u + 2]) * cf);
-                        den[u] = ab * cf;
-                    }
+                        for (int u = 0; u < 4; ++u) {
+                            const float ab = (1.0f + ev[4 * u + 0]) * (1.0f + ev[4 * u + 2]), cf = 1.0f + ev[4 * u + 1];
+                            num[u] = fmaf(cst[c][4 * half + u], ab, (1.0f - ev[4 * u + 2]) * cf);
+                            den[u] = rcp_approx(ab * cf);
+                        }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) den[u] = rcp_approx(den[u]);
+                        for (int u = 0; u < 4; ++u) {
+                            cst[c][4 * half + u] = num[u] * den[u];
+                            num[u] = ex2_approx(fminf(cst[c][4 * half + u] * (-2.0f * LOG2E), EX2_CLAMP));   // e_c
+                        }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        cst[c][u] = num[u] * den[u];
-                        num[u] = ex2_approx(fminf(cst[c][u] * (-2.0f * LOG2E), EX2_CLAMP));              // e_c
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) den[u] = rcp_approx((1.0f + ev[4 * u + 3]) * (1.0f + num[u]));
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) hv[u] = (1.0f - num[u]) * den[u];
+                        for (int u = 0; u < 4; ++u) hv[u] = (1.0f - num[u]) * rcp_approx((1.0f + ev[4 * u + 3]) * (1.0f + num[u]));
 
-                    const int j = 4 * c + s;                   // k-group of units 32c + 8s .. + 7
-                    if (final_f32) {
-                        if (c >= NCH / 2 && c < NCH - 1) mbar_wait(&bars[BAR_ACC_READY + NCH - 1], ph_acc);   // every MMA of the step retired
-                        float* dst = reinterpret_cast<float*>(c < NCH / 2 ? sAh_next : sAh_prev) + ((8 * j) % (H / 2)) * ROWS + row_l;
+                        const int j = 4 * c + s;               // k-group of units 32c + 8s .. + 7
+                        if (final_f32) {
+                            if (half == 0 && c >= NCH / 2 && c < NCH - 1) mbar_wait(&bars[BAR_ACC_READY + NCH - 1], ph_acc);   // every MMA retired
+                            float* dst = reinterpret_cast<float*>(c < NCH / 2 ? sAh_next : sAh_prev) + ((8 * j) % (H / 2) + 4 * half) * ROWS + row_l;
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) dst[u * ROWS] = hv[u];
-                    } else {
-                        *reinterpret_cast<uint4*>(sAh_next + unit_offset(ROWS, row_l, j)) =
-                            make_uint4(pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]), pack_half2(hv[4], hv[5]), pack_half2(hv[6], hv[7]));
-                    }
-                    if (t + 1 < T) {                           // publish this chunk's slice of h_t: its K-slice of the next
-                        fence_proxy_async_smem();              // recurrent product can be issued while later chunks still run
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_leader(&bars[BAR_H_READY + c], rank);
-                    }
-                    if (warp == 0) APE_TRACE(0, t, 3 + 3 * c);
-                    if (a.out_units && APE_EXP != 4) {
-                        const float os = a.out_scale;
-                        a.out_units[((((size_t)tile * T + t) * 2 + rank) * KG + j) * ROWS + row_l] =
-                            make_uint4(pack_half2(hv[0] * os, hv[1] * os), pack_half2(hv[2] * os, hv[3] * os),
-                                       pack_half2(hv[4] * os, hv[5] * os), pack_half2(hv[6] * os, hv[7] * os));
+                            for (int u = 0; u < 4; ++u) dst[u * ROWS] = hv[u];
+                        } else if (half == 1) {
+                            *reinterpret_cast<uint4*>(sAh_next + unit_offset(ROWS, row_l, j)) =
+                                make_uint4(pack_half2(hlo[0], hlo[1]), pack_half2(hlo[2], hlo[3]), pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]));
+                        }
+                        if (half == 1) {
+                            if (t + 1 < T) {                   // publish this chunk's slice of h_t: its K-slice of the next recurrent
+                                fence_proxy_async_smem();      // product can be issued while later chunks still run
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_leader(&bars[BAR_H_READY + c], rank);
+                            }
+                            if (warp == 0) APE_TRACE(0, t, 3 + 3 * c);
+                            if (a.out_units && APE_EXP != 4) {
+                                const float os = a.out_scale;
+                                a.out_units[((((size_t)tile * T + t) * 2 + rank) * KG + j) * ROWS + row_l] =
+                                    make_uint4(pack_half2(hlo[0] * os, hlo[1] * os), pack_half2(hlo[2] * os, hlo[3] * os),
+                                               pack_half2(hv[0] * os, hv[1] * os), pack_half2(hv[2] * os, hv[3] * os));
+                            }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) hlo[u] = hv[u];
+                        }
                     }
                 }
                 ph_acc ^= 1;
