@@ -6,7 +6,7 @@
 
 namespace ape {
 
-constexpr int FEAT_ROWS_PER_CTA = 128;
+constexpr int FEAT_ROWS_PER_CTA = 32;    // latency-bound fp64 row math: small CTAs spread a frame of ~1k rows over more SMs
 
 struct SmemRow {                       // indexable view of one staged row (odd stride -> no bank conflicts)
     const float* p;

@@ -306,6 +306,8 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline,
         "checksum": checksum,
     }
+    if rank == 0 and world == 1 and not args.no_realtime:
+        line["realtime"] = realtime_latency(BatchedEstimator, N, syn)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         workers = max(1, min(os.cpu_count() or 1, 64))
         ref = CpuReference(kind, n, smooth, workers)
@@ -321,6 +323,27 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def realtime_latency(BatchedEstimator, N, syn, frames=300):
+    """BASELINE configs[1]: watch+phone pocket LSTM estimator, 1 stream x 100 MC samples, per-frame latency through the
+    host-facing call (one 55-float row in pinned memory -> message + std + 100 sample positions back on the host)."""
+    kind = syn.KIND_POCKET
+    spec = syn.kind_spec(kind)
+    state = syn.synth_state_dict(spec["I"], spec["H"], spec["L"], spec["O"], 1234 + kind)
+    be = BatchedEstimator(kind=kind, layout=spec["layout"], state=state, seq_len=spec["T"], y_targets=spec["y_targets"],
+                          stats=spec["stats"], n_streams=1, mc_samples=100, smooth=1, dropout=spec["p"], frames_per_call=1,
+                          mask_mode=N.MASK_PHILOX, philox_seed=7)
+    rows = syn.synth_rows(kind, 1, frames + 20, config_id=2)
+    lat = []
+    for f in range(frames + 20):
+        t0 = time.perf_counter()
+        be.step(rows[:, f:f + 1])
+        lat.append(time.perf_counter() - t0)
+    lat = np.asarray(lat[20:]) * 1e3
+    return {"workload": "watch+phone pocket LSTM estimator (I22 H256 L2 T6 O14), 1 stream x 100 MC samples, frame by frame",
+            "lstm_variant": be.lstm_variant, "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+            "frames": frames, "timing": "host wall clock around BatchedEstimator.step (H2D + 3 stages + D2H + sync)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,6 +354,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=400, help="frames per worker of the bounded cpu_baseline sample")
     ap.add_argument("--ref-frames", type=int, default=100, help="--impl reference: frames per worker per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-realtime", action="store_true", help="skip the configs[1] single-stream latency leg")
     ap.add_argument("--lstm", default="auto", choices=["auto", "fp32", "tc"], help="LSTM kernel variant (auto: probe-gated tensor cores)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
