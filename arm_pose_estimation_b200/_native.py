@@ -50,6 +50,7 @@ class LstmArgs(C.Structure):
         ("all_steps", C.c_int),
         ("weights_tc", C.c_void_p),
         ("layer_ms", C.c_void_p),
+        ("layer_begin", C.c_int), ("layer_end", C.c_int), ("ws_parity", C.c_int),
         ("trace", C.c_void_p),
         ("trace_layer", C.c_int),
     ]

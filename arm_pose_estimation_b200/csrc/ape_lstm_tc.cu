@@ -481,7 +481,7 @@ extern "C" int ape_mc_lstm_tc_workspace_bytes(int I, int H, int L, int T, int O,
     const uint64_t rpc0 = tc_rpc0(E);
     const uint64_t tiles0 = ((uint64_t)E + 2 * rpc0 - 1) / (2 * rpc0), tiles1 = ((uint64_t)E * n_samples + 255) / 256;
     const uint64_t u0 = (tiles0 * 256 * T * H * 2 + 255) & ~(uint64_t)255, u1 = (tiles1 * 256 * T * H * 2 + 255) & ~(uint64_t)255;
-    *bytes = u0 + (L > 3 ? 2 : (L > 2 ? 1 : 0)) * u1 + 512;
+    *bytes = 2 * u0 + (L > 3 ? 2 : (L > 2 ? 1 : 0)) * u1 + 512;            // two copies of layer 0's output (ws_parity)
     return APE_OK;
 }
 
@@ -505,23 +505,27 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
     const size_t u0 = ((size_t)tiles0 * 256 * g->T * g->H * 2 + 255) & ~(size_t)255;
     const size_t u1 = ((size_t)tiles1 * 256 * g->T * g->H * 2 + 255) & ~(size_t)255;
     char* wsp = (char*)(((uintptr_t)g->workspace + 255) & ~(uintptr_t)255);
-    uint4* units0 = (uint4*)wsp;                                        // layer 0 output, one row per estimate
-    uint4* units[2] = {(uint4*)(wsp + u0), (uint4*)(wsp + u0 + u1)};    // layers >= 1 outputs, one row per (estimate, sample)
+    uint4* units0 = (uint4*)(wsp + (g->ws_parity & 1) * u0);            // layer 0 output, one row per estimate (two copies)
+    uint4* units[2] = {(uint4*)(wsp + 2 * u0), (uint4*)(wsp + 2 * u0 + u1)};   // layers >= 1 outputs, one row per (estimate, sample)
+    const int l_begin = (g->layer_begin == 0 && g->layer_end == 0) ? 0 : g->layer_begin;
+    const int l_end = (g->layer_begin == 0 && g->layer_end == 0) ? g->L : g->layer_end;
+    if (l_begin < 0 || l_end > g->L || l_begin >= l_end) return APE_ERR_BAD_ARG;
 
     cudaEvent_t ev[17] = {};
-    const bool prof = g->layer_ms != nullptr && g->L <= 16;
+    const bool prof = g->layer_ms != nullptr && g->L <= 16 && l_begin == 0 && l_end == g->L;
     if (prof) for (int l = 0; l <= g->L; ++l) APE_CUDA_TRY(cudaEventCreate(&ev[l]));
     if (prof) APE_CUDA_TRY(cudaEventRecord(ev[0], st));
 
     const int H = g->H;
     const uint8_t* wl = (const uint8_t*)g->weights_tc;
     const float scale = g->mask_mode == APE_MASK_NONE ? 1.0f : 1.0f / (1.0f - g->dropout_p);
-    for (int l = 0; l < g->L; ++l) {
+    for (int l = 0; l < l_end; ++l) {
         const bool last = l == g->L - 1;
         tc::TcLayerArgs a{};
         a.W = wl;
         a.bias_s = (const float*)(wl + tc_layer_bytes(l, g->I, H) - (size_t)4 * H * 4);
         wl += tc_layer_bytes(l, g->I, H);
+        if (l < l_begin) continue;
         a.T = g->T;
         a.kgx = tc_kgx(l, g->I, H);
         a.Kin = l == 0 ? g->I : H;

@@ -11,6 +11,8 @@ of the stream axis (``shard_streams``) with no collective.
 """
 from dataclasses import dataclass
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -18,6 +20,8 @@ from arm_pose_estimation_b200 import _native as N
 from arm_pose_estimation_b200.data_types.bone_map import body_measurements_row
 from arm_pose_estimation_b200.estimate import nn_models
 from arm_pose_estimation_b200.utility.names import NNS_TARGETS
+
+C_void = ctypes.c_void_p
 
 TARGET_IDS = {
     NNS_TARGETS.ORI_CAL_LARM_UARM: N.TARGET_ORI_CAL_LARM_UARM,
@@ -98,7 +102,7 @@ class BatchedEstimator:
     def __init__(self, kind, layout, state, seq_len, y_targets, stats, n_streams, mc_samples,
                  smooth=1, dropout=0.2, bonemap=None, frames_per_call=1, emit_samples=True, normalize=True,
                  mask_mode=N.MASK_PHILOX, philox_seed=0, first_stream=0, device=None,
-                 lstm_variant="auto", tc_min_rows=4096, tc_tolerance_m=5e-5):
+                 lstm_variant="auto", tc_min_rows=4096, tc_tolerance_m=5e-5, pipeline=True):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedEstimator needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = N.load()
@@ -172,6 +176,12 @@ class BatchedEstimator:
                 self.tc_probe_error_m = self._probe_tc_error()
                 if lstm_variant == "tc" or self.tc_probe_error_m <= tc_tolerance_m:
                     self.lstm_variant = "tc"
+            # cross-call software pipeline (tensor-core path): stage 1 + LSTM layer 0 of call k+1 (a few dozen CTAs) run on a
+            # side stream under the tail of call k's big layer kernels; layer 0's output is double-buffered by call parity
+            self.pipeline = bool(pipeline) and self.lstm_variant == "tc"
+            self.side_stream = torch.cuda.Stream(device=dev) if self.pipeline else None
+            self.l1_done = [None, None]
+        self.calls = 0
         self.frame = 0
         self.launches = 0             # kernels launched so far (bench.py reports it)
 
@@ -223,18 +233,19 @@ class BatchedEstimator:
         self.frame = 0
 
     # ---- device path -----------------------------------------------------------------------------------
-    def step_device(self, raw, n_frames=None, masks=None, layer_ms=None, trace=None, trace_layer=1):
-        """``raw``: device tensor ``[B, nF, ncols]`` float32 (nF <= frames_per_call).  Enqueues the three stages
-        on the current stream and returns an ``EstimateBatch`` of views into the estimator's device buffers."""
+    def step_device(self, raw, n_frames=None, masks=None, layer_ms=None, trace=None, trace_layer=1, raw_ready=False,
+                    _h2d_from=None):
+        """``raw``: device tensor ``[B, nF, ncols]`` float32 (nF <= frames_per_call).  Enqueues the three stages and returns an
+        ``EstimateBatch`` of views into the estimator's device buffers (valid until the call after next).  ``raw_ready=True``
+        promises that ``raw`` is already materialised (not pending on the current stream), which lets the pipelined path
+        start stage 1 + layer 0 of this call under the previous call's kernels."""
         nF = int(raw.shape[1]) if n_frames is None else int(n_frames)
         if raw.shape[0] != self.B or nF > self.nF_max or raw.shape[2] != self.ncols or not raw.is_contiguous():
             raise UserWarning(f"raw rows must be a contiguous [B={self.B}, nF<={self.nF_max}, {self.ncols}] tensor, got {tuple(raw.shape)}")
         if raw.dtype != torch.float32:
             raise UserWarning("raw rows must be float32 (the wire format, messaging.py)")
-        lib, st, B = self.lib, N.current_stream_ptr(), self.B
-        N.check(lib.ape_features(N.ptr(raw), self.layout, self.kind, N.ptr(self.xx_m), N.ptr(self.xx_s),
-                                 1 if self.normalize else 0, N.ptr(self.feats), B, nF, self.frame, self.feat_ring, st),
-                "ape_features")
+        lib, B = self.lib, self.B
+        main = torch.cuda.current_stream()
         a = N.LstmArgs()
         a.weights = self.weights.data_ptr()
         a.I, a.H, a.L, a.T, a.O = self.I, self.H, self.L, self.T, self.O
@@ -258,12 +269,48 @@ class BatchedEstimator:
             a.layer_ms = layer_ms.ctypes.data
         if trace is not None:                        # debugging: device int64[768] of SM-clock stamps (tensor-core path)
             a.trace, a.trace_layer = trace.data_ptr(), trace_layer
-        N.check(self._lstm_fn()(a, st), "ape_mc_lstm")
+
+        def features(stream_ptr):
+            N.check(lib.ape_features(N.ptr(raw), self.layout, self.kind, N.ptr(self.xx_m), N.ptr(self.xx_s),
+                                     1 if self.normalize else 0, N.ptr(self.feats), B, nF, self.frame, self.feat_ring, stream_ptr),
+                    "ape_features")
+
+        if self.pipeline and layer_ms is None and trace is None:
+            side, parity = self.side_stream, self.calls & 1
+            if not raw_ready and _h2d_from is None:
+                ev_in = torch.cuda.Event()
+                ev_in.record(main)
+                side.wait_event(ev_in)               # raw may still be pending on the caller's stream
+            if self.l1_done[parity] is not None:
+                side.wait_event(self.l1_done[parity])    # layer 1 of call k-2 has finished reading this copy of layer 0's output
+            with torch.cuda.stream(side):
+                if _h2d_from is not None:
+                    raw.copy_(_h2d_from, non_blocking=True)
+                sp = C_void(side.cuda_stream)
+                features(sp)
+                a.layer_begin, a.layer_end, a.ws_parity = 0, 1, parity
+                N.check(lib.ape_mc_lstm_tc(a, sp), "ape_mc_lstm_tc (layer 0)")
+                ev0 = torch.cuda.Event()
+                ev0.record(side)
+            main.wait_event(ev0)
+            st = N.current_stream_ptr()
+            a.layer_begin, a.layer_end = 1, self.L
+            N.check(lib.ape_mc_lstm_tc(a, st), "ape_mc_lstm_tc (layers >= 1)")
+            ev1 = torch.cuda.Event()
+            ev1.record(main)
+            self.l1_done[parity] = ev1
+        else:
+            if _h2d_from is not None:
+                raw.copy_(_h2d_from, non_blocking=True)
+            st = N.current_stream_ptr()
+            features(st)
+            N.check(self._lstm_fn()(a, st), "ape_mc_lstm")
         N.check(lib.ape_fk_reduce(N.ptr(self.preds), self.pred_ring, N.ptr(self.yy_m), N.ptr(self.yy_s), N.ptr(self.body),
                                   self.target, self.O, B, nF, self.frame, self.n, self.smooth,
                                   N.ptr(self.msg), N.ptr(self.samples), N.ptr(self.std), None, N.ptr(self.status), st),
                 "ape_fk_reduce")
         self.launches += 2 + self.L
+        self.calls += 1
         out = EstimateBatch(self._view(self.msg, nF), self._view(self.std, nF), self._view(self.samples, nF),
                             self._view(self.status, nF), self.frame)
         self.frame += nF
@@ -296,12 +343,11 @@ class BatchedEstimator:
             stage = self.raw_host[slot].view(-1)[: E * self.ncols].view(self.B, nF, self.ncols)
             stage.numpy()[...] = rows
             raw = self.raw.view(-1)[: E * self.ncols].view(self.B, nF, self.ncols)
-            raw.copy_(stage, non_blocking=True)
             main = torch.cuda.current_stream()
             self._use_out(slot)
             if self.copy_done[slot] is not None:
                 main.wait_event(self.copy_done[slot])     # device buffer `slot` has been read back (call k-2)
-            out = self.step_device(raw, nF, masks)
+            out = self.step_device(raw, nF, masks, _h2d_from=stage)
             computed = torch.cuda.Event()
             computed.record(main)
             host, dev_out = self.out_host[slot], self.out_all

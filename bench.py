@@ -230,12 +230,12 @@ def run_ours(args, rank, world, local_rank):
         while not clk.lines and time.time() - t_wait < 10.0:  # nvidia-smi start-up must not land in the timed region
             time.sleep(0.05)
         for f in range(W):
-            be.step_device(frames_dev[f])
+            be.step_device(frames_dev[f], raw_ready=True)
         barrier()
         launches0 = be.launches
         ev0.record()
         for f in range(W, W + K):
-            be.step_device(frames_dev[f])
+            be.step_device(frames_dev[f], raw_ready=True)     # inputs resident in HBM before the timed region
         ev1.record()
         barrier()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))

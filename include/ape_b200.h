@@ -108,6 +108,9 @@ typedef struct ape_lstm_args {
     /* profiling: null, or L floats on the HOST - the call then brackets every layer launch with CUDA events,
        synchronises the stream and writes each layer's device time in milliseconds (bench.py's roofline leg) */
     float* layer_ms;
+    /* tensor-core path: run only layers [layer_begin, layer_end) (0, 0 = all) so a caller can put layer 0 of the next call
+       on a second stream under the tail of this call; ws_parity (0 | 1) selects one of two copies of layer 0's output */
+    int layer_begin, layer_end, ws_parity;
     /* debugging (tensor-core path): null, or a device buffer of 768 int64 that receives SM-clock stamps of the first
        tile of CTA 0 of layer `trace_layer` ([role: epilogue, loader, issuer][step < 16][event < 16]) */
     void* trace;
