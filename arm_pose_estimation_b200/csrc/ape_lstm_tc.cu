@@ -242,9 +242,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         const int j = 4 * c + s;               // k-group of units 32c + 8s .. + 7
                         if (final_f32) {
                             if (half == 0 && c >= NCH / 2 && c < NCH - 1) mbar_wait(&bars[BAR_ACC_READY + NCH - 1], ph_acc);   // every MMA retired
-                            float* dst = reinterpret_cast<float*>(c < NCH / 2 ? sAh_next : sAh_prev) + ((8 * j) % (H / 2) + 4 * half) * ROWS + row_l;
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) dst[u * ROWS] = hv[u];
+                            // fp32 h_T as [row][H/2 units], 16-byte groups XOR-swizzled by the row so both this store and the
+                            // output layer's 128-bit reads are bank-conflict free
+                            const int grp = ((8 * j) % (H / 2)) / 4 + half;
+                            float4* dst = reinterpret_cast<float4*>(c < NCH / 2 ? sAh_next : sAh_prev) + row_l * (H / 8) + (grp ^ (row_l & (H / 8 - 1)));
+                            *dst = make_float4(hv[0], hv[1], hv[2], hv[3]);
                         } else if (half == 1) {
                             *reinterpret_cast<uint4*>(sAh_next + unit_offset(ROWS, row_l, j)) =
                                 make_uint4(pack_half2(hlo[0], hlo[1]), pack_half2(hlo[2], hlo[3]), pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]));
@@ -270,25 +272,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 }
                 ph_acc ^= 1;
                 if (final_f32) {                               // output_layer (nn_models.py:189), last step only
+                    if (warp == 0) APE_TRACE(0, t, 13);
                     epi_bar_sync();
                     if (valid) {
                         const int e = row / a.n, smp = row - e * a.n;
                         const int b = e / a.nF, f = a.frame0 + e % a.nF;
-                        const float* h0 = reinterpret_cast<const float*>(sAh_next) + row_l;
-                        const float* h1 = reinterpret_cast<const float*>(sAh_prev) + row_l;
-                        for (int o = s; o < a.O; o += 4) {
-                            const float* w = a.Wo + (size_t)o * H;
-                            float sum = __ldg(a.bo + o);
-#pragma unroll 8
-                            for (int k = 0; k < H / 2; ++k) sum = fmaf(__ldg(w + k), h0[k * ROWS], sum);
-#pragma unroll 8
-                            for (int k = 0; k < H / 2; ++k) sum = fmaf(__ldg(w + H / 2 + k), h1[k * ROWS], sum);
-                            float* dst = a.preds + (((size_t)b * a.pred_ring + f % a.pred_ring) * a.n_out) * a.O + o;
-                            if (a.n == 1 && a.n_out > 1) for (int s2 = 0; s2 < a.n_out; ++s2) dst[(size_t)s2 * a.O] = sum;
-                            else dst[(size_t)smp * a.O] = sum;
+                        // this thread: outputs o = s, s+4, ... of its row (<= 5 for O <= 20), all accumulated in one sweep over k
+                        // so every h value is read from shared memory once and the FMA chains are independent
+                        float acc[5];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) acc[i] = (s + 4 * i < a.O) ? __ldg(a.bo + s + 4 * i) : 0.0f;
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {
+                            const float4* hp = reinterpret_cast<const float4*>(part == 0 ? sAh_next : sAh_prev) + row_l * (H / 8);
+                            const float* wp = a.Wo + part * (H / 2);
+#pragma unroll 4
+                            for (int gk = 0; gk < H / 8; ++gk) {
+                                const float4 x = hp[gk ^ (row_l & (H / 8 - 1))];
+#pragma unroll
+                                for (int i = 0; i < 5; ++i) {
+                                    if (s + 4 * i < a.O) {
+                                        const float4 w = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(s + 4 * i) * H + 4 * gk));
+                                        acc[i] = fmaf(w.x, x.x, acc[i]); acc[i] = fmaf(w.y, x.y, acc[i]);
+                                        acc[i] = fmaf(w.z, x.z, acc[i]); acc[i] = fmaf(w.w, x.w, acc[i]);
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            const int o = s + 4 * i;
+                            if (o < a.O) {
+                                float* dst = a.preds + (((size_t)b * a.pred_ring + f % a.pred_ring) * a.n_out) * a.O + o;
+                                if (a.n == 1 && a.n_out > 1) for (int s2 = 0; s2 < a.n_out; ++s2) dst[(size_t)s2 * a.O] = acc[i];
+                                else dst[(size_t)smp * a.O] = acc[i];
+                            }
                         }
                     }
                     epi_bar_sync();                            // the next tile's first cell update rewrites these tiles
+                    if (warp == 0) APE_TRACE(0, t, 14);
                 }
             }
         }
@@ -472,7 +494,7 @@ extern "C" int ape_lstm_tc_blob_bytes(int I, int H, int L, int64_t* bytes) {
 }
 
 extern "C" int ape_mc_lstm_tc_supported(int I, int H, int L, int O) {
-    return ((H == 64 || H == 128) && L >= 2 && I >= 1 && ape_pack_kin_pad(0, I, H) <= H && O >= 1) ? 1 : 0;
+    return ((H == 64 || H == 128) && L >= 2 && I >= 1 && ape_pack_kin_pad(0, I, H) <= H && O >= 1 && O <= 20) ? 1 : 0;
 }
 
 extern "C" int ape_mc_lstm_tc_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes) {

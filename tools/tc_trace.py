@@ -21,7 +21,7 @@ be.step_device(rows[:, 3:4].contiguous(), trace=trace, trace_layer=layer)
 torch.cuda.synchronize()
 tr = trace.cpu().numpy().reshape(3, 16, 16)
 t0 = tr[tr > 0].min()
-names = {0: ["step top"] + [f"{e} c{c}" for c in range(4) for e in ("ACC_READY seen", "drained", "h published")],
+names = {0: ["step top"] + [f"{e} c{c}" for c in range(4) for e in ("ACC_READY seen", "drained", "h published")] + ["output layer start", "output layer done"],
          1: ["loads issued", "masks applied", "X_DONE seen", "X_READY arrived"],
          2: ["top", "X_READY seen"] + [f"{e} c{c}" for c in range(4) for e in ("SLOT_FREE seen", "x+old pieces issued", "H_READY seen")] + ["step issued"]}
 for role, rn in enumerate(["epilogue warp 0 (chunk 0)", "loader warp", "MMA issuer"]):
