@@ -222,6 +222,151 @@ class DropoutLSTM:
         return self._run(x, n_samples, N.MASK_PHILOX)
 
 
+def ff_dims(state):
+    """(I, H, Lh, O) from the reference's feed-forward state-dict keys."""
+    H, I = state["_input_layer.weight"].shape
+    Lh = sum(1 for k in state if k.startswith("_hidden_layers.") and k.endswith(".weight"))
+    return int(I), int(H), int(Lh), int(state["_output_layer.weight"].shape[0])
+
+
+def pack_ff_weights(state):
+    """Reference ``DropoutFF`` / ``DropoutFF2D`` state dict -> flat float32 blob of ``csrc/ape_ff.cu``: dense layers transposed
+    (``W^T [K][H]`` then bias) so threads over output units read them coalesced, the output layer as is."""
+    st = {k: np.asarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
+          for k, v in state.items()}
+    I, H, Lh, O = ff_dims(st)
+    parts = [st["_input_layer.weight"].T.ravel(), st["_input_layer.bias"]]
+    for l in range(Lh):
+        parts += [st[f"_hidden_layers.{l}.weight"].T.ravel(), st[f"_hidden_layers.{l}.bias"]]
+    parts += [st["_output_layer.weight"].ravel(), st["_output_layer.bias"]]
+    return np.ascontiguousarray(np.concatenate([np.ascontiguousarray(p).ravel() for p in parts]), dtype=np.float32)
+
+
+class _DropoutSwitch:
+    """Stand-in for the ``model._do`` dropout sub-module: only its train / eval switch matters (nn_models.py:364)."""
+
+    def __init__(self):
+        self.training = False
+
+    def train(self, mode=True):
+        self.training = bool(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+
+class DropoutFF:
+    """MC-dropout feed-forward regressor behind the reference API (``nn_models.py:313-370``): ``forward(x)``,
+    ``monte_carlo_predictions(n_samples, x)``; the hidden stack runs once per input row, the output layer per sample."""
+
+    def __init__(self, output_size, hidden_layer_size, hidden_layer_count, input_size, dropout=0.2, philox_seed=None):
+        self.output_size = int(output_size)
+        self.input_size = int(input_size)
+        self.hidden_layer_size = int(hidden_layer_size)
+        self.hidden_layer_count = int(hidden_layer_count)
+        self.dropout = float(dropout)
+        self._do = _DropoutSwitch()
+        self.philox_seed = int(torch.initial_seed() if philox_seed is None else philox_seed) & (2 ** 64 - 1)
+        self._calls = 0
+        self._state = None
+        self._blob = None
+
+    def _flat_inputs(self):
+        return self.input_size
+
+    def load_state_dict(self, state):
+        I, H, Lh, O = ff_dims(state)
+        if (I, H, Lh, O) != (self._flat_inputs(), self.hidden_layer_size, self.hidden_layer_count, self.output_size):
+            raise RuntimeError(f"state dict is for (I,H,Lh,O)={(I, H, Lh, O)}, model is "
+                               f"{(self._flat_inputs(), self.hidden_layer_size, self.hidden_layer_count, self.output_size)}")
+        self._state = {k: torch.as_tensor(np.asarray(v.detach().cpu() if isinstance(v, torch.Tensor) else v, dtype=np.float32))
+                       for k, v in state.items()}
+        self._blob = None
+        return self
+
+    def state_dict(self):
+        return dict(self._state)
+
+    def eval(self):
+        self._do.eval()
+        return self
+
+    def train(self, mode=True):
+        self._do.train(mode)
+        return self
+
+    def _run(self, x2d, n_samples, mask_mode, masks=None):
+        _require_cuda()
+        if self._state is None:
+            raise UserWarning("model has no weights: call load_state_dict first")
+        if self._blob is None:
+            self._blob = torch.from_numpy(pack_ff_weights(self._state)).cuda()
+        host_in = not x2d.is_cuda
+        xd = x2d.detach().to(device="cuda", dtype=torch.float32).contiguous()
+        rows = int(xd.shape[0])
+        H, O = self.hidden_layer_size, self.output_size
+        preds = torch.empty((rows, n_samples, O), dtype=torch.float32, device="cuda")
+        md = None
+        if mask_mode == N.MASK_INJECTED:
+            md = torch.as_tensor(np.asarray(masks) if not isinstance(masks, torch.Tensor) else masks)
+            md = md.to(device="cuda", dtype=torch.uint8).contiguous()
+            if md.numel() != rows * n_samples * H:
+                raise UserWarning(f"masks must hold rows*n*H = {rows * n_samples * H} entries, got {md.numel()}")
+        N.check(N.load().ape_mc_ff(N.ptr(self._blob), self._flat_inputs(), H, self.hidden_layer_count, O, self.dropout,
+                                   N.ptr(xd), rows, n_samples, mask_mode, N.ptr(md), self.philox_seed, 0,
+                                   self._calls & 0x7FFFFFFF, N.ptr(preds), N.current_stream_ptr()), "ape_mc_ff")
+        self._calls += 1
+        return preds.cpu() if host_in else preds
+
+    def _flatten(self, x):
+        return x.reshape(-1, self.input_size)
+
+    def forward(self, x):
+        """``x [..., input] -> [..., output]`` (nn_models.py:338-353); dropout is active only after ``train()`` / an MC call."""
+        lead = tuple(x.shape[:-1])
+        out = self._run(self._flatten(x), 1, N.MASK_PHILOX if self._do.training else N.MASK_NONE)
+        return out.reshape(*lead, self.output_size)
+
+    __call__ = forward
+
+    def monte_carlo_predictions(self, n_samples, x, masks=None):
+        """``x [1, input] -> [n_samples, 1, output]`` with the output dropout active (nn_models.py:355-370)."""
+        if x.shape[0] > 1:
+            raise UserWarning("MC predictions only for batch size 1")
+        self._do.train()
+        out = self._run(self._flatten(x), n_samples, N.MASK_INJECTED if masks is not None else N.MASK_PHILOX, masks)
+        return out.reshape(n_samples, 1, self.output_size)
+
+
+class DropoutFF2D(DropoutFF):
+    """``DropoutFF`` on the flattened ``[seq_len, input]`` window (``nn_models.py:252-310``)."""
+
+    def __init__(self, output_size, hidden_layer_size, hidden_layer_count, input_size, seq_len, dropout=0.2, philox_seed=None):
+        super().__init__(output_size, hidden_layer_size, hidden_layer_count, input_size, dropout, philox_seed)
+        self.seq_len = int(seq_len)
+
+    def _flat_inputs(self):
+        return self.input_size * self.seq_len
+
+    def _flatten(self, x):
+        return x.reshape(x.shape[0], -1)
+
+    def forward(self, x):
+        out = self._run(self._flatten(x), 1, N.MASK_PHILOX if self._do.training else N.MASK_NONE)
+        return out.reshape(x.shape[0], self.output_size)
+
+    __call__ = forward
+
+    def monte_carlo_predictions(self, n_samples, x, masks=None):
+        """``x [1, seq_len, input] -> [n_samples, 1, output]`` (nn_models.py:294-310: the flattened row is repeated as [n,1,*])."""
+        if x.shape[0] > 1:
+            raise UserWarning("MC predictions only for batch size 1")
+        self._do.train()
+        out = self._run(self._flatten(x), n_samples, N.MASK_INJECTED if masks is not None else N.MASK_PHILOX, masks)
+        return out.reshape(n_samples, 1, self.output_size)
+
+
 def load_deployed_model_from_hash(hash_str: str):
     """``(model, params)`` from ``<deploy>/nn/<hash>/{results.json, checkpoint.pt}`` (nn_models.py:373-415);
     the checkpoint is the ``(model_state, optimizer_state)`` tuple the reference saves."""
@@ -235,6 +380,8 @@ def load_deployed_model_from_hash(hash_str: str):
         params = json.load(f)
     if params["model"] == "DropoutLSTM":
         params["model"] = DropoutLSTM
+    elif params["model"] == "DropoutFF":
+        params["model"] = DropoutFF
     else:
         raise UserWarning(f"{params['model']} not handled")
     nn_model = params["model"](

@@ -136,6 +136,19 @@ int ape_mc_lstm_tc(const ape_lstm_args* args, void* stream);
 int ape_philox_masks(uint64_t philox_seed, uint32_t stream_id0, int B, int nF, int frame0, int L, int T,
                      int n_samples, int H, float dropout_p, uint8_t* masks, void* stream);
 
+/*
+ * MC-dropout feed-forward regressors (DropoutFF / DropoutFF2D, nn_models.py:252-370): Linear + leaky_relu stack evaluated once
+ * per input row, dropout + output layer once per MC sample.
+ *   blob   packed by pack_ff_weights(): layer 0 W^T [I][H], b [H]; Lh x (W^T [H][H], b [H]); output W [O][H], b [O]
+ *   x      [rows][I] float32 (DropoutFF2D: the flattened [seq_len * input] window)
+ *   masks  APE_MASK_INJECTED: [rows][n_samples][H] of {0,1}
+ *   preds  [rows][n_samples][O] float32
+ */
+int ape_ff_blob_floats(int I, int H, int Lh, int O, int64_t* floats);
+int ape_mc_ff(const float* blob, int I, int H, int Lh, int O, float dropout_p, const float* x, int rows,
+              int n_samples, int mask_mode, const uint8_t* masks, uint64_t philox_seed, uint32_t stream_id0,
+              uint32_t frame0, float* preds, void* stream);
+
 /* ---- stage 3: targets -> quaternions + forward kinematics + MC reduction ----------------------- */
 /*
  * Replaces the de-normalisation of estimator.py:108-109, the smoothing stack of :112-118,

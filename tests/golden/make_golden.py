@@ -267,15 +267,51 @@ def golden_e2e():
                             weight_seed=1234 + kind)
 
 
+def golden_ff():
+    print("feed-forward MC regressors: DropoutFF / DropoutFF2D with the dropout mask torch drew")
+    from oracle import ff as OFF
+    out = {}
+    for name, ctor, x_shape in (("ff", lambda: ref_nn.DropoutFF(output_size=12, hidden_layer_size=96, hidden_layer_count=2, input_size=20, dropout=0.2), (1, 20)),
+                                ("ff2d", lambda: ref_nn.DropoutFF2D(output_size=14, hidden_layer_size=64, hidden_layer_count=1, input_size=22, seq_len=5, dropout=0.3), (1, 5, 22))):
+        torch.manual_seed(77)
+        model = ctor().eval()
+        p = model._do.p
+        state = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+        rng = np.random.default_rng(5)
+        x = rng.normal(size=x_shape).astype(np.float32)
+        xb = rng.normal(size=(6,) + x_shape[1:]).astype(np.float32)
+        n = 40
+        H = state["_input_layer.weight"].shape[0]
+        with torch.no_grad():
+            y_eval = model(torch.from_numpy(xb)).numpy()
+            torch.manual_seed(4321)
+            y_mc = model.monte_carlo_predictions(n_samples=n, x=torch.from_numpy(x)).numpy()
+            # the mask torch drew: nn.Dropout on the [n, 1, H] activations, replayed from the same seed
+            torch.manual_seed(4321)
+            masks = torch.empty(n, 1, H).bernoulli_(1 - p).numpy().astype(np.uint8).reshape(n, H)
+        model.eval()
+        close(OFF.forward_with_masks(state, xb.reshape(6, -1)), y_eval.reshape(6, -1), 2e-6, f"{name} eval")
+        close(OFF.forward_with_masks(state, np.repeat(x.reshape(1, -1), n, 0), masks, p), y_mc.reshape(n, -1), 2e-6, f"{name} mc n={n}")
+        out.update({f"{name}__x": x, f"{name}__xb": xb, f"{name}__y_eval": y_eval, f"{name}__y_mc": y_mc, f"{name}__masks": masks,
+                    f"{name}__p": np.float32(p)})
+        out.update({f"{name}__state__{k}": v for k, v in state.items()})
+    np.savez_compressed(HERE / "ff.npz", **out)
+
+
 def main():
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     with tempfile.TemporaryDirectory() as tmp:
         make_ref_deploy(tmp)
+        if only == "ff":
+            golden_ff()
+            return
         golden_tables()
         golden_quat()
         golden_features()
         golden_fk()
         golden_lstm()
         golden_e2e()
+        golden_ff()
     print("fixtures written to", HERE)
 
 
