@@ -359,12 +359,13 @@ class DropoutFF2D(DropoutFF):
     __call__ = forward
 
     def monte_carlo_predictions(self, n_samples, x, masks=None):
-        """``x [1, seq_len, input] -> [n_samples, 1, output]`` (nn_models.py:294-310: the flattened row is repeated as [n,1,*])."""
+        """``x [1, seq_len, input] -> [n_samples, output]`` (nn_models.py:294-310: the repeated rows are flattened again by
+        ``forward``, so the sample axis is the only leading axis)."""
         if x.shape[0] > 1:
             raise UserWarning("MC predictions only for batch size 1")
         self._do.train()
         out = self._run(self._flatten(x), n_samples, N.MASK_INJECTED if masks is not None else N.MASK_PHILOX, masks)
-        return out.reshape(n_samples, 1, self.output_size)
+        return out.reshape(n_samples, self.output_size)
 
 
 def load_deployed_model_from_hash(hash_str: str):
