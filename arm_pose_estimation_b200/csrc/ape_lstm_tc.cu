@@ -223,7 +223,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                             ev[4 * u + 0] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 0]), -LOG2E, bs.x), EX2_CLAMP));
                             ev[4 * u + 1] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 1]), -LOG2E, bs.y), EX2_CLAMP));
                             ev[4 * u + 2] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 2]), -2.0f * LOG2E, bs.z), EX2_CLAMP));
-                            ev[4 * u + 3] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 3]), -LOG2E, bs.w), EX2_CLAMP));
+                            // (o gate unclamped: an infinite e_o only makes the reciprocal below 0; e_c is finite since |c| <= T)
+                            ev[4 * u + 3] = ex2_approx(fmaf(__uint_as_float(r[4 * u + 3]), -LOG2E, bs.w));
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -234,7 +235,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             cst[c][4 * half + u] = num[u] * den[u];
-                            num[u] = ex2_approx(fminf(cst[c][4 * half + u] * (-2.0f * LOG2E), EX2_CLAMP));   // e_c
+                            num[u] = ex2_approx(cst[c][4 * half + u] * (-2.0f * LOG2E));   // e_c = 2^(-2c log2e), |c| <= T: no overflow
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) hv[u] = (1.0f - num[u]) * rcp_approx((1.0f + ev[4 * u + 3]) * (1.0f + num[u]));
@@ -512,6 +513,7 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
     int rc = check_lstm_args(g);
     if (rc != APE_OK) return rc;
     if (!ape_mc_lstm_tc_supported(g->I, g->H, g->L, g->O) || g->all_steps) return APE_ERR_UNSUPPORTED;
+    if (g->T > 40) return APE_ERR_UNSUPPORTED;                 // |c_t| <= t keeps 2^(2 c log2e) finite in fp32 only for T <= 44
     if (!g->weights_tc) return APE_ERR_BAD_ARG;
     const long long E = (long long)g->B * g->nF;
     if (E == 0) return APE_OK;

@@ -164,7 +164,7 @@ class BatchedEstimator:
             self.lstm_variant = "fp32"
             if lstm_variant not in ("auto", "fp32", "tc"):
                 raise UserWarning(f"lstm_variant must be 'auto', 'fp32' or 'tc', got {lstm_variant!r}")
-            tc_ok = N.tc_supported(self.I, self.H, self.L, self.O)
+            tc_ok = N.tc_supported(self.I, self.H, self.L, self.O) and self.T <= 40
             if lstm_variant == "tc" and not tc_ok:
                 raise UserWarning(f"the tensor-core LSTM kernel does not support H={self.H}, L={self.L}")
             if lstm_variant == "tc" or (lstm_variant == "auto" and tc_ok and B * nF * self.n >= tc_min_rows):
