@@ -76,15 +76,19 @@ struct SliceCursor {
     }
 };
 
-template <int RT>
+// NCH_REG = 0: cell state in shared memory, any H % 32 == 0.  NCH_REG = H / 32 > 0: the chunk loop is unrolled and the cell
+// state lives in registers (RT x 2 values per chunk), which frees H*R floats of shared memory - H = 256 then fits 64-row
+// tiles (twice the FFMA : LDS ratio of the 32-row tiles it would otherwise get).
+template <int RT, int NCH_REG>
 __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerArgs a) {
     constexpr int R = 16 * RT;
     extern __shared__ __align__(16) float smem[];
     const int H = a.H, T = a.T;
     float* xt = smem;                               // [Kin_pad][R]  this step's (masked, scaled) input
     float* hbuf = xt + a.Kin_pad * R;               // [2][H][R]     h_{t-1} / h_t
-    float* cbuf = hbuf + 2 * H * R;                 // [H][R]        cell state
-    float* ws = cbuf + H * R;                       // [W_STAGES][KS][CHUNK_COLS] weight ring
+    float* cbuf = hbuf + 2 * H * R;                 // [H][R]        cell state (NCH_REG == 0 only)
+    float* ws = cbuf + (NCH_REG > 0 ? 0 : H * R);   // [W_STAGES][KS][CHUNK_COLS] weight ring
+    float creg[NCH_REG > 0 ? NCH_REG : 1][2][RT];   // cell state in registers (NCH_REG > 0)
 
     const int tid = threadIdx.x, cg = tid & 15, rg = tid >> 4;
     const int tile = blockIdx.x, row0 = tile * R;
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerAr
         float* hnxt = hbuf + (cur ^ 1) * H * R;
         const int ns = nsx + (t > 0 ? nsh : 0);
 
-        for (int chunk = 0; chunk < nchunks; ++chunk) {
+        auto chunk_body = [&](const int chunk, float (&cst)[2][RT]) {
             float acc[RT][8];
             {
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bp + chunk * CHUNK_COLS + cg * 4));
@@ -210,7 +214,12 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerAr
             for (int half = 0; half < 2; ++half) {
                 const int u = chunk * CHUNK_UNITS + cg + 16 * half;
                 float cv[RT], hv[RT];
-                if (t > 0) ld_vec<RT>(cbuf + u * R + rg * RT, cv);
+                if (NCH_REG > 0) {
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) cv[r] = cst[half][r];
+                } else if (t > 0) {
+                    ld_vec<RT>(cbuf + u * R + rg * RT, cv);
+                }
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
                     const float gi = sigmoid_f(acc[r][4 * half + 0]), gf = sigmoid_f(acc[r][4 * half + 1]);
@@ -219,9 +228,20 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerAr
                     cv[r] = c;
                     hv[r] = go * tanh_f(c);
                 }
-                st_vec<RT>(cbuf + u * R + rg * RT, cv);
+                if (NCH_REG > 0) {
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) cst[half][r] = cv[r];
+                } else {
+                    st_vec<RT>(cbuf + u * R + rg * RT, cv);
+                }
                 st_vec<RT>(hnxt + u * R + rg * RT, hv);
             }
+        };
+        if (NCH_REG > 0) {
+#pragma unroll
+            for (int chunk = 0; chunk < (NCH_REG > 0 ? NCH_REG : 1); ++chunk) chunk_body(chunk, creg[chunk]);
+        } else {
+            for (int chunk = 0; chunk < nchunks; ++chunk) chunk_body(chunk, creg[0]);
         }
         __syncthreads();                                               // h_t complete
 
@@ -277,23 +297,27 @@ __global__ void philox_masks_kernel(uint64_t seed, uint32_t stream_id0, int nF, 
 
 // ---- host side -----------------------------------------------------------------------------------------
 
+// rt >= 8 encodes "RT = 4 with the cell state in registers" (only instantiated for H = 256)
+static size_t layer_smem_bytes(int rt, int H, int kin_pad) {
+    const bool regc = rt >= 8;
+    const int r = 16 * (regc ? 4 : rt);
+    return sizeof(float) * ((size_t)r * (kin_pad + (regc ? 2 : 3) * H) + W_STAGES * W_STAGE_FLOATS);
+}
 static int max_rt_for(int H, int kin_pad_max) {
-    for (int rt = 4; rt >= 1; rt >>= 1) {
-        const size_t bytes = sizeof(float) * ((size_t)16 * rt * (kin_pad_max + 3 * H) + W_STAGES * W_STAGE_FLOATS);
-        if (bytes <= 227 * 1024) return rt;
-    }
+    if (layer_smem_bytes(4, H, kin_pad_max) <= 227 * 1024) return 4;
+    if (H == 256 && layer_smem_bytes(8, H, kin_pad_max) <= 227 * 1024) return 8;
+    for (int rt = 2; rt >= 1; rt >>= 1)
+        if (layer_smem_bytes(rt, H, kin_pad_max) <= 227 * 1024) return rt;
     return 0;
 }
-// rows per tile = 16 * rt: the largest tile shared memory allows, shrunk while the grid would leave SMs idle
+static int rows_per_tile(int rt) { return 16 * (rt >= 8 ? 4 : rt); }
+// rows per tile: the largest tile shared memory allows, shrunk while the grid would leave SMs idle
 static int pick_rt(long long rows, int H, int kin_pad) {
     int rt = max_rt_for(H, kin_pad);
-    while (rt > 1 && (rows + 16 * rt - 1) / (16 * rt) < 148) rt >>= 1;
+    while (rt > 1 && (rows + rows_per_tile(rt) - 1) / rows_per_tile(rt) < 148) rt = rt >= 8 ? 2 : rt >> 1;
     return rt;
 }
-static size_t layer_smem_bytes(int rt, int H, int kin_pad) {
-    return sizeof(float) * ((size_t)16 * rt * (kin_pad + 3 * H) + W_STAGES * W_STAGE_FLOATS);
-}
-static long long tiles_of(long long rows, int rt) { return (rows + 16 * rt - 1) / (16 * rt); }
+static long long tiles_of(long long rows, int rt) { return (rows + rows_per_tile(rt) - 1) / rows_per_tile(rt); }
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 int make_plan(int I, int H, int L, int T, long long E, int n, FmaPlan* p) {
@@ -304,22 +328,23 @@ int make_plan(int I, int H, int L, int T, long long E, int n, FmaPlan* p) {
     p->rt1 = pick_rt(E * n, H, H);
     p->tiles0 = tiles_of(E, p->rt0);
     p->tiles1 = tiles_of(E * n, p->rt1);
-    p->seq0_bytes = L > 1 ? align256((size_t)p->tiles0 * T * H * 16 * p->rt0 * sizeof(float)) : 0;
-    p->seq1_bytes = L > 2 ? align256((size_t)p->tiles1 * T * H * 16 * p->rt1 * sizeof(float)) : 0;
+    p->seq0_bytes = L > 1 ? align256((size_t)p->tiles0 * T * H * rows_per_tile(p->rt0) * sizeof(float)) : 0;
+    p->seq1_bytes = L > 2 ? align256((size_t)p->tiles1 * T * H * rows_per_tile(p->rt1) * sizeof(float)) : 0;
     p->total = p->seq0_bytes + (L > 3 ? 2 : 1) * p->seq1_bytes;
     return APE_OK;
 }
 
-template <int RT> static int launch_layer(const LayerArgs& a, long long tiles, cudaStream_t st) {
-    const size_t smem = layer_smem_bytes(RT, a.H, a.Kin_pad);
-    APE_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_fma_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lstm_layer_fma_kernel<RT><<<(unsigned)tiles, LSTM_THREADS, smem, st>>>(a);
+template <int RT, int NCH_REG> static int launch_layer(int rt_code, const LayerArgs& a, long long tiles, cudaStream_t st) {
+    const size_t smem = layer_smem_bytes(rt_code, a.H, a.Kin_pad);
+    APE_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_fma_kernel<RT, NCH_REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_layer_fma_kernel<RT, NCH_REG><<<(unsigned)tiles, LSTM_THREADS, smem, st>>>(a);
     return check_launch();
 }
 static int launch_layer_rt(int rt, const LayerArgs& a, long long tiles, cudaStream_t st) {
-    if (rt == 4) return launch_layer<4>(a, tiles, st);
-    if (rt == 2) return launch_layer<2>(a, tiles, st);
-    return launch_layer<1>(a, tiles, st);
+    if (rt == 8) return launch_layer<4, 8>(rt, a, tiles, st);
+    if (rt == 4) return launch_layer<4, 0>(rt, a, tiles, st);
+    if (rt == 2) return launch_layer<2, 0>(rt, a, tiles, st);
+    return launch_layer<1, 0>(rt, a, tiles, st);
 }
 
 int check_lstm_args(const ape_lstm_args* g) {
@@ -365,7 +390,7 @@ int fma_launch_layer(const ape_lstm_args* g, int l, const FmaPlan& p, const floa
     } else {
         a.in_mode = l == 1 ? IN_SHARED : IN_TILED;
         a.in = seq_in;
-        a.in_R = 16 * p.rt0;
+        a.in_R = rows_per_tile(p.rt0);
         a.rows = (int)(E * g->n_samples); a.n = g->n_samples;
         rt = p.rt1; tiles = p.tiles1;
     }
