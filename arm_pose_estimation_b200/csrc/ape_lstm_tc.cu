@@ -24,6 +24,7 @@
 #include "ape_lstm_pack.h"
 #include "ape_lstm_plan.cuh"
 #include "ape_umma.cuh"
+#include "ape_lstm_tc_args.cuh"
 
 namespace ape {
 namespace tc {
@@ -33,60 +34,8 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS;
 constexpr int THREADS = (MMA_WARP + 1) * 32;       // 16 epilogue + 8 operand-loader + 1 MMA-issue warps = 800
 constexpr int ROWS = 128;                          // rows per CTA = TMEM lanes
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float EX2_CLAMP = 40.0f;                 // (1 + 2^40)^3 still fits fp32
 
-enum { IN_WINDOW_F32 = 0, IN_DENSE_F32 = 1, IN_SHARED_UNITS = 2, IN_UNITS = 3 };
 enum { BAR_X_READY = 0, BAR_X_DONE = 1, BAR_ACC_READY = 2, BAR_SLOT_FREE = 6, BAR_H_READY = 10, BAR_COUNT = 14 };
-
-struct TcLayerArgs {
-    const uint8_t* W;          // this layer: [cta 2][chunk][x k-groups then h k-groups][64 gate columns][8 halfs]
-    const float* bias_s;       // [4H] column c = 4u+g, pre-multiplied by -log2(e) (i, f, o) / -2 log2(e) (g)
-    int T, kgx, Kin;           // x-part: kgx k-groups (layer 0: ceil16(I)/8, else H/8) of which Kin columns are real
-    int rpc;                   // rows per CTA actually used (128, or 32 to spread a small layer 0 over more SMs)
-    int in_rpc_shift;          // IN_SHARED_UNITS: log2(rpc) of the producing layer
-    int in_mode;
-    const void* in;
-    int feat_ring, nF, frame0, rows, n;
-    int mask_mode;
-    const uint8_t* masks;
-    int gap, n_gaps;
-    uint64_t seed;
-    uint32_t stream_id0;
-    uint32_t keep_thr16;
-    uint4* out_units;          // [pair tile][T][cta][k-group][128 rows] 16-byte units of fp16 (h_t * out_scale), or null
-    float out_scale;           // the consumer's 1/(1-p): scaling BEFORE the fp16 rounding keeps it a single rounding
-    const float* Wo;
-    const float* bo;
-    int O;
-    float* preds;
-    int pred_ring, n_out;
-    int n_pair_tiles;
-    long long* trace;          // debugging: null, or [3 roles][16 steps][16 events] SM-clock stamps of the first tile of CTA 0
-};
-
-#ifndef APE_EXP
-#define APE_EXP 0            // timing experiments only (tools/tc_experiments.sh); 0 = the real kernel
-#endif
-#if APE_EXP == 2
-__device__ __forceinline__ float ex2_approx(float x) { return x * 0.99f; }
-__device__ __forceinline__ float rcp_approx(float x) { return x * 1.01f; }
-#else
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-#endif
-
-// One LSTM cell from the four ex2 ARGUMENTS  p = -(gate + bias) * log2e  (g gate: * 2 log2e):
-//   i*g~ = (1 - e_g) / ((1 + e_i)(1 + e_g)),  f = 1 / (1 + e_f)  share one reciprocal; h = o * tanh(c) another.
-__device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po, float& c, float& h) {
-    const float ei = ex2_approx(fminf(pi, EX2_CLAMP)), ef = ex2_approx(fminf(pf, EX2_CLAMP));
-    const float eg = ex2_approx(fminf(pg, EX2_CLAMP)), eo = ex2_approx(fminf(po, EX2_CLAMP));
-    const float ab = (1.0f + ei) * (1.0f + eg), cf = 1.0f + ef;
-    const float num = fmaf(c, ab, (1.0f - eg) * cf);
-    c = num * rcp_approx(ab * cf);
-    const float ec = ex2_approx(fminf(c * (-2.0f * LOG2E), EX2_CLAMP));
-    h = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
-}
 
 // role 0 = epilogue warp 0 (chunk 0), role 1 = loader warp 16, role 2 = MMA issuer; only block 0, first tile, lane 0
 #define APE_TRACE(role, t, ev) do { if (a.trace && blockIdx.x == 0 && tile == cluster_id && lane == 0 && (t) < 16) \
@@ -495,7 +444,7 @@ extern "C" int ape_lstm_tc_blob_bytes(int I, int H, int L, int64_t* bytes) {
 }
 
 extern "C" int ape_mc_lstm_tc_supported(int I, int H, int L, int O) {
-    return ((H == 64 || H == 128) && L >= 2 && I >= 1 && ape_pack_kin_pad(0, I, H) <= H && O >= 1 && O <= 20) ? 1 : 0;
+    return ((H == 64 || H == 128 || ape::tcs::supported(H)) && L >= 2 && I >= 1 && ape_pack_kin_pad(0, I, H) <= H && O >= 1 && O <= 20) ? 1 : 0;
 }
 
 extern "C" int ape_mc_lstm_tc_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes) {
@@ -582,7 +531,7 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
         a.preds = last ? g->preds : nullptr;
         a.pred_ring = g->pred_ring; a.n_out = g->n_samples;
         a.trace = (g->trace && l == g->trace_layer) ? (long long*)g->trace : nullptr;
-        rc = H == 128 ? tc::launch<128>(a, sm_count, st) : tc::launch<64>(a, sm_count, st);
+        rc = H == 128 ? tc::launch<128>(a, sm_count, st) : H == 64 ? tc::launch<64>(a, sm_count, st) : tcs::launch_layer(H, a, sm_count, st);
         if (rc != APE_OK) return rc;
         if (prof) APE_CUDA_TRY(cudaEventRecord(ev[l + 1], st));
     }

@@ -1,0 +1,73 @@
+// Shared between the two tensor-core MC-LSTM layer kernels: ape_lstm_tc.cu (gate weights resident in shared memory,
+// H <= 128) and ape_lstm_tcs.cu (gate weights streamed from L2 through a TMA ring, H = 256): the per-layer argument
+// block, the input modes and the transcendental helpers of the cell update.
+#pragma once
+#include "ape_common.cuh"
+#include "ape_umma.cuh"
+
+namespace ape {
+namespace tc {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float EX2_CLAMP = 40.0f;                 // (1 + 2^40)^3 still fits fp32
+
+enum { IN_WINDOW_F32 = 0, IN_DENSE_F32 = 1, IN_SHARED_UNITS = 2, IN_UNITS = 3 };
+
+struct TcLayerArgs {
+    const uint8_t* W;          // this layer: [cta 2][chunk][x k-groups then h k-groups][64 gate columns][8 halfs]
+    const float* bias_s;       // [4H] column c = 4u+g, pre-multiplied by -log2(e) (i, f, o) / -2 log2(e) (g)
+    int T, kgx, Kin;           // x-part: kgx k-groups (layer 0: ceil16(I)/8, else H/8) of which Kin columns are real
+    int rpc;                   // rows per CTA actually used (128, or 32 to spread a small layer 0 over more SMs)
+    int in_rpc_shift;          // IN_SHARED_UNITS: log2(rpc) of the producing layer
+    int in_mode;
+    const void* in;
+    int feat_ring, nF, frame0, rows, n;
+    int mask_mode;
+    const uint8_t* masks;
+    int gap, n_gaps;
+    uint64_t seed;
+    uint32_t stream_id0;
+    uint32_t keep_thr16;
+    uint4* out_units;          // [pair tile][T][cta][k-group][128 rows] 16-byte units of fp16 (h_t * out_scale), or null
+    float out_scale;           // the consumer's 1/(1-p): scaling BEFORE the fp16 rounding keeps it a single rounding
+    const float* Wo;
+    const float* bo;
+    int O;
+    float* preds;
+    int pred_ring, n_out;
+    int n_pair_tiles;
+    long long* trace;          // debugging: null, or [3 roles][16 steps][16 events] SM-clock stamps of the first tile of CTA 0
+};
+
+#ifndef APE_EXP
+#define APE_EXP 0            // timing experiments only (tools/tc_experiments.sh); 0 = the real kernel
+#endif
+#if APE_EXP == 2
+__device__ __forceinline__ float ex2_approx(float x) { return x * 0.99f; }
+__device__ __forceinline__ float rcp_approx(float x) { return x * 1.01f; }
+#else
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+
+// One LSTM cell from the four ex2 ARGUMENTS  p = -(gate + bias) * log2e  (g gate: * 2 log2e):
+//   i*g~ = (1 - e_g) / ((1 + e_i)(1 + e_g)),  f = 1 / (1 + e_f)  share one reciprocal; h = o * tanh(c) another.
+__device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po, float& c, float& h) {
+    const float ei = ex2_approx(fminf(pi, EX2_CLAMP)), ef = ex2_approx(fminf(pf, EX2_CLAMP));
+    const float eg = ex2_approx(fminf(pg, EX2_CLAMP)), eo = ex2_approx(fminf(po, EX2_CLAMP));
+    const float ab = (1.0f + ei) * (1.0f + eg), cf = 1.0f + ef;
+    const float num = fmaf(c, ab, (1.0f - eg) * cf);
+    c = num * rcp_approx(ab * cf);
+    const float ec = ex2_approx(fminf(c * (-2.0f * LOG2E), EX2_CLAMP));
+    h = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
+}
+
+
+}  // namespace tc
+
+namespace tcs {
+// streamed-weights kernel (ape_lstm_tcs.cu)
+bool supported(int H);
+int launch_layer(int H, const tc::TcLayerArgs& a, int sm_count, cudaStream_t st);
+}  // namespace tcs
+}  // namespace ape

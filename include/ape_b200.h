@@ -122,7 +122,8 @@ int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_
 int ape_mc_lstm_fma(const ape_lstm_args* args, void* stream);
 /*
  * Tensor-core variant (tcgen05, cta_group::2, TMEM accumulators): fp16 operands, fp32 accumulation and cell state.
- * H in {64, 128}, L >= 2, all_steps == 0; same arguments and outputs as ape_mc_lstm_fma plus weights_tc.
+ * H in {64, 128} (gate weights resident in shared memory) or 256 (gate weights streamed from L2 through a TMA ring),
+ * L >= 2, all_steps == 0; same arguments and outputs as ape_mc_lstm_fma plus weights_tc.
  * Use when the streams x MC-samples batch is large (>= a few thousand rows); the fp32 variant is the exact path.
  */
 int ape_mc_lstm_tc_supported(int I, int H, int L, int O);
@@ -185,7 +186,8 @@ int ape_selfcheck_keep8(uint64_t seed, uint32_t stream, uint32_t frame, uint32_t
 int ape_selfcheck_features(int kind, int layout, const float* row, double* xx, int* n_features);
 int ape_selfcheck_row_pose(int target, const double* preds, const double* body9, int use_float, double* est, int* bad);
 /* GPU self-test of the tcgen05 / TMEM plumbing: D[128*cta_group][N] (f32) = A * B^T with f16 operands packed in the
- * canonical K-major no-swizzle layout of csrc/ape_umma.cuh (a_packed: [cta][K/8][128][8], b_packed: [cta][K/8][N/cta][8]). */
+ * canonical K-major no-swizzle layout of csrc/ape_umma.cuh (a_packed: [cta][K/8][128][8], b_packed: [cta][K/8][N/cta][8]).
+ * cta_group 1 | 2; + 16 routes the A operand through tensor memory (tcgen05.st, then the [a_tmem] form of tcgen05.mma). */
 int ape_selftest_umma(const void* a_packed, const void* b_packed, float* d, int N, int K, int cta_group, void* stream);
 
 #ifdef __cplusplus

@@ -80,10 +80,10 @@ def test_auto_variant_selection():
     assert small.lstm_variant == "fp32"
     big, _, _ = make(syn.KIND_UARM, 256, 100, "auto")                   # 25600 rows -> tensor cores, if the probe passes
     assert big.lstm_variant == "tc" and big.tc_probe_error_m <= 5e-5
-    wide, _, _ = make(syn.KIND_POCKET, 256, 100, "auto")                # H = 256: not supported by the pair kernel -> fp32
-    assert wide.lstm_variant == "fp32"
-    with pytest.raises(UserWarning):
-        make(syn.KIND_POCKET, 4, 10, "tc")
+    wide, _, _ = make(syn.KIND_POCKET, 256, 100, "auto")                # H = 256: the streamed-weights tensor-core kernel
+    assert wide.lstm_variant == "tc" and wide.tc_probe_error_m <= 5e-5
+    with pytest.raises(UserWarning):                                    # H = 32 has no tensor-core kernel
+        make(syn.KIND_UARM, 4, 10, "tc", state=syn.synth_state_dict(38, 32, 2, 12, 3))
 
 
 def test_tc_repeated_runs_are_bit_identical():
@@ -94,6 +94,59 @@ def test_tc_repeated_runs_are_bit_identical():
     be, _, _ = make(kind, B, n, "tc", mask_mode=N.MASK_PHILOX, philox_seed=5)
     ref_msg = ref_smp = None
     for rep in range(25):
+        be.reset()
+        be.step(rows[:, 0:1])
+        out = be.step(rows[:, 1:2])
+        if ref_msg is None:
+            ref_msg, ref_smp = out.msg.copy(), out.samples.copy()
+            assert np.isfinite(ref_msg).all() and np.isfinite(ref_smp).all()
+        else:
+            np.testing.assert_array_equal(out.msg, ref_msg)
+            np.testing.assert_array_equal(out.samples, ref_smp)
+
+
+# ---- H = 256 (watch-only and pocket models): CTA-pair kernel with streamed weights and the cell state in TMEM ------------
+
+@pytest.mark.parametrize("name", ["watch_only_s3", "pocket_s1"])
+def test_tc256_whole_path_against_reference_messages(name):
+    g = load_golden(f"e2e_{name}.npz")
+    kind = {"watch_only": syn.KIND_WATCH_ONLY, "pocket": syn.KIND_POCKET}[name.rsplit("_", 1)[0]]
+    n, smooth = int(g["n"]), int(g["smooth"])
+    masks = unpack_masks(g)
+    rows, F = g["rows"], len(g["rows"])
+    be, spec, _ = make(kind, 1, n, "tc", smooth=smooth, frames_per_call=F, mask_mode=N.MASK_INJECTED)
+    assert be.lstm_variant == "tc" and spec["H"] == 256
+    out = be.step(rows[None], masks=masks[None])
+    worst = msg_close(out.msg[0], g["msgs"][:, :25])
+    err = np.abs(out.samples[0].reshape(F, -1) - g["msgs"][:, 25:]).max()
+    assert err <= POS_TOL
+    print(f"{name} streamed-weights tensor-core path: worst position error vs the reference's messages {max(worst, err):.3g} m "
+          f"(probe {be.tc_probe_error_m:.3g} m)")
+
+
+@pytest.mark.parametrize("kind,B", [(syn.KIND_POCKET, 200), (syn.KIND_WATCH_ONLY, 3)])
+def test_tc256_matches_fp32_kernel_with_philox(kind, B):
+    # 200 x 100 rows = 79 pair tiles > 74 clusters: the persistent tile loop (and the weight ring) wraps; 3 x 100 = 300 rows:
+    # a ragged second tile
+    n = 100
+    rows = np.tile(syn.synth_rows(kind, 8, 3, config_id=6), (25, 1, 1))[:B]
+    a, _, _ = make(kind, B, n, "tc", mask_mode=N.MASK_PHILOX, philox_seed=78)
+    b, _, _ = make(kind, B, n, "fp32", mask_mode=N.MASK_PHILOX, philox_seed=78)
+    worst = 0.0
+    for f in range(3):
+        oa, ob = a.step(rows[:, f:f + 1]), b.step(rows[:, f:f + 1])
+        worst = max(worst, float(np.abs(oa.samples - ob.samples).max()), msg_close(oa.msg, ob.msg))
+        np.testing.assert_allclose(oa.std, ob.std, rtol=0.02, atol=2e-6)
+    print(f"H=256 tensor-core vs fp32 kernel, same Philox masks, {B * n} rows x 3 frames: worst position difference {worst:.3g} m")
+    assert worst <= POS_TOL
+
+
+def test_tc256_repeated_runs_are_bit_identical():
+    kind, B, n = syn.KIND_WATCH_ONLY, 1024, 100
+    rows = np.tile(syn.synth_rows(kind, 32, 2, config_id=9), (32, 1, 1))
+    be, _, _ = make(kind, B, n, "tc", mask_mode=N.MASK_PHILOX, philox_seed=6)
+    ref_msg = ref_smp = None
+    for rep in range(10):
         be.reset()
         be.step(rows[:, 0:1])
         out = be.step(rows[:, 1:2])
