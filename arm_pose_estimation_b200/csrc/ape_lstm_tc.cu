@@ -161,19 +161,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         const float4* bias4 = reinterpret_cast<const float4*>(sBias + (c * 32 + 8 * s + 4 * half) * 4);
                         // the 4 cells advance in lock-step through the transcendental stages (independent MUFU ops back to back):
                         //   e = 2^-(gate+bias)  ->  i*g~ and f share one reciprocal  ->  2^(-2c)  ->  h = o * tanh(c)
-                        float ev[16], hv[4], num[4], den[4];
+                        float hv[4];
+#if APE_TC_TANH
+                        // 5 MUFU per cell: sigmoid(x) = 0.5 + 0.5 tanh(x / 2) with the hardware tanh (see ape_lstm_tc_args.cuh)
+                        float tg[16];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-#if APE_EXP == 5
-                            const float4 bs = make_float4(0.1f, 0.2f, 0.3f, 0.4f);
+                            const float4 bs = bias4[u];            // 0.5 b (i, f, o), b (g)
+                            tg[4 * u + 0] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 0]), 0.5f, bs.x));
+                            tg[4 * u + 1] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 1]), 0.5f, bs.y));
+                            tg[4 * u + 2] = tanh_approx(__uint_as_float(r[4 * u + 2]) + bs.z);
+                            tg[4 * u + 3] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 3]), 0.5f, bs.w));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float gi = fmaf(tg[4 * u + 0], 0.5f, 0.5f), gf = fmaf(tg[4 * u + 1], 0.5f, 0.5f);
+                            cst[c][4 * half + u] = fmaf(gf, cst[c][4 * half + u], gi * tg[4 * u + 2]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) hv[u] = fmaf(tg[4 * u + 3], 0.5f, 0.5f) * tanh_approx(cst[c][4 * half + u]);
 #else
-                            const float4 bs = bias4[u];
-#endif
-                            ev[4 * u + 0] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 0]), -LOG2E, bs.x), EX2_CLAMP));
-                            ev[4 * u + 1] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 1]), -LOG2E, bs.y), EX2_CLAMP));
-                            ev[4 * u + 2] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 2]), -2.0f * LOG2E, bs.z), EX2_CLAMP));
+                        float ev[16], num[4], den[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 bs = bias4[u];            // 0.5 b (i, f, o), b (g) -> -log2e (gate + b), g: -2 log2e (gate + b)
+                            ev[4 * u + 0] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 0]), -LOG2E, bs.x * (-2.0f * LOG2E)), EX2_CLAMP));
+                            ev[4 * u + 1] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 1]), -LOG2E, bs.y * (-2.0f * LOG2E)), EX2_CLAMP));
+                            ev[4 * u + 2] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 2]), -2.0f * LOG2E, bs.z * (-2.0f * LOG2E)), EX2_CLAMP));
                             // (o gate unclamped: an infinite e_o only makes the reciprocal below 0; e_c is finite since |c| <= T)
-                            ev[4 * u + 3] = ex2_approx(fmaf(__uint_as_float(r[4 * u + 3]), -LOG2E, bs.w));
+                            ev[4 * u + 3] = ex2_approx(fmaf(__uint_as_float(r[4 * u + 3]), -LOG2E, bs.w * (-2.0f * LOG2E)));
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -188,6 +204,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) hv[u] = (1.0f - num[u]) * rcp_approx((1.0f + ev[4 * u + 3]) * (1.0f + num[u]));
+#endif
 
                         const int j = 4 * c + s;               // k-group of units 32c + 8s .. + 7
                         if (final_f32) {
@@ -428,6 +445,7 @@ template <int H> static int launch(const TcLayerArgs& a, int sm_count, cudaStrea
 }  // namespace ape
 
 // rows per CTA of layer 0 (one row per estimate): a small batch is spread over more CTA pairs, 32 rows each
+constexpr int TC_MAX_SMS = 160;                    // cell-state scratch is sized for this many CTAs (B200: 148)
 static int tc_rpc0(long long E) { return E >= 16384 ? 128 : 32; }
 static int tc_kgx(int layer, int I, int H) { return layer == 0 ? ape_pack_kin_pad(0, I, H) / 8 : H / 8; }
 static size_t tc_layer_bytes(int layer, int I, int H) {
@@ -454,6 +472,8 @@ extern "C" int ape_mc_lstm_tc_workspace_bytes(int I, int H, int L, int T, int O,
     const uint64_t tiles0 = ((uint64_t)E + 2 * rpc0 - 1) / (2 * rpc0), tiles1 = ((uint64_t)E * n_samples + 255) / 256;
     const uint64_t u0 = (tiles0 * 256 * T * H * 2 + 255) & ~(uint64_t)255, u1 = (tiles1 * 256 * T * H * 2 + 255) & ~(uint64_t)255;
     *bytes = 2 * u0 + (L > 3 ? 2 : (L > 2 ? 1 : 0)) * u1 + 512;            // two copies of layer 0's output (ws_parity)
+    // streamed-weights kernel: two regions of per-CTA cell-state scratch (layer 0 may run on a side stream under a layer >= 1)
+    *bytes += 2 * (uint64_t)ape::tcs::scratch_bytes(H, TC_MAX_SMS);
     return APE_OK;
 }
 
@@ -478,6 +498,12 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
     const size_t u0 = ((size_t)tiles0 * 256 * g->T * g->H * 2 + 255) & ~(size_t)255;
     const size_t u1 = ((size_t)tiles1 * 256 * g->T * g->H * 2 + 255) & ~(size_t)255;
     char* wsp = (char*)(((uintptr_t)g->workspace + 255) & ~(uintptr_t)255);
+    // streamed-weights kernel (H = 256): two regions of per-CTA cell-state scratch at the front (a position that does not
+    // depend on the call's size: layer 0 of the next call may run on a side stream under a layer >= 1 of this one)
+    char* scratch = wsp;
+    const size_t scratch_region = tcs::scratch_bytes(g->H, TC_MAX_SMS);
+    if (scratch_region && sm_count > TC_MAX_SMS) return APE_ERR_UNSUPPORTED;
+    wsp += 2 * scratch_region;
     uint4* units0 = (uint4*)(wsp + (g->ws_parity & 1) * u0);            // layer 0 output, one row per estimate (two copies)
     uint4* units[2] = {(uint4*)(wsp + 2 * u0), (uint4*)(wsp + 2 * u0 + u1)};   // layers >= 1 outputs, one row per (estimate, sample)
     const int l_begin = (g->layer_begin == 0 && g->layer_end == 0) ? 0 : g->layer_begin;
@@ -530,6 +556,7 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
         a.O = g->O;
         a.preds = last ? g->preds : nullptr;
         a.pred_ring = g->pred_ring; a.n_out = g->n_samples;
+        a.cstate = scratch_region ? (float*)(scratch + (l == 0 ? 0 : scratch_region)) : nullptr;
         a.trace = (g->trace && l == g->trace_layer) ? (long long*)g->trace : nullptr;
         rc = H == 128 ? tc::launch<128>(a, sm_count, st) : H == 64 ? tc::launch<64>(a, sm_count, st) : tcs::launch_layer(H, a, sm_count, st);
         if (rc != APE_OK) return rc;

@@ -15,7 +15,7 @@ enum { IN_WINDOW_F32 = 0, IN_DENSE_F32 = 1, IN_SHARED_UNITS = 2, IN_UNITS = 3 };
 
 struct TcLayerArgs {
     const uint8_t* W;          // this layer: [cta 2][chunk][x k-groups then h k-groups][64 gate columns][8 halfs]
-    const float* bias_s;       // [4H] column c = 4u+g, pre-multiplied by -log2(e) (i, f, o) / -2 log2(e) (g)
+    const float* bias_s;       // [4H] column c = 4u+g, scaled for the tanh form: 0.5 b (i, f, o), b (g)
     int T, kgx, Kin;           // x-part: kgx k-groups (layer 0: ceil16(I)/8, else H/8) of which Kin columns are real
     int rpc;                   // rows per CTA actually used (128, or 32 to spread a small layer 0 over more SMs)
     int in_rpc_shift;          // IN_SHARED_UNITS: log2(rpc) of the producing layer
@@ -36,8 +36,19 @@ struct TcLayerArgs {
     float* preds;
     int pred_ring, n_out;
     int n_pair_tiles;
+    float* cstate;             // streamed-weights kernel (H = 256): per-CTA cell-state scratch, tcs::scratch_bytes() bytes
     long long* trace;          // debugging: null, or [3 roles][16 steps][16 events] SM-clock stamps of the first tile of CTA 0
 };
+
+// Cell-update arithmetic of both tensor-core kernels.  APE_TC_TANH = 1 (default): every gate through the hardware tanh
+// (tanh.approx.f32; sigmoid(x) = 0.5 + 0.5 tanh(x / 2)) - 5 MUFU and ~10 FP32 ops per cell.  0: the exp2 / reciprocal form
+// (7 MUFU, ~19 FP32 ops; i * g~ and f share one reciprocal), kept for A/B measurements.  Measured on B200: the tanh form is
+// 6 % (H = 256) faster per layer and the position error against the fp32 kernel is unchanged (it is set by
+// the fp16 operand rounding).  The bias in the fp16 blob is stored ready for the tanh form: 0.5 b (i, f, o), b (g).
+#ifndef APE_TC_TANH
+#define APE_TC_TANH 1
+#endif
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 #ifndef APE_EXP
 #define APE_EXP 0            // timing experiments only (tools/tc_experiments.sh); 0 = the real kernel
@@ -68,6 +79,7 @@ __device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po
 namespace tcs {
 // streamed-weights kernel (ape_lstm_tcs.cu)
 bool supported(int H);
+size_t scratch_bytes(int H, int sm_count);      // one region of per-CTA cell-state scratch (a launch needs one)
 int launch_layer(int H, const tc::TcLayerArgs& a, int sm_count, cudaStream_t st);
 }  // namespace tcs
 }  // namespace ape

@@ -58,12 +58,11 @@ def pack_lstm_weights_tc(state):
     of the chunk's 128 (n = 4 * u_local + g, i.e. units 16 r .. 16 r + 15 with gates i, f, g, o interleaved) as
     K-major no-swizzle tiles ``[k-group][64][8]`` halfs - first the input weights (layer 0: K zero-padded to a
     multiple of 16), then the recurrent weights; after both CTAs the bias ``b_ih + b_hh`` in column order 4u + g,
-    pre-multiplied by -log2(e) (i, f, o) or -2 log2(e) (g) so the epilogue's sigmoid / tanh arguments come out of
-    one FMA."""
+    scaled for the epilogue's ``sigmoid(x) = 0.5 + 0.5 tanh(x / 2)`` form: 0.5 b for i, f, o and b for g, so every
+    tanh argument comes out of one FMA."""
     st = {k: np.asarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
           for k, v in state.items()}
     I, H, L, O = lstm_dims(st)
-    log2e = np.float32(1.4426950408889634)
     parts = []
     nl = np.arange(64)
 
@@ -81,8 +80,7 @@ def pack_lstm_weights_tc(state):
                 rows = (n % 4) * H + 32 * c + n // 4
                 parts += [tile(w_ih, rows, kin_pad), tile(w_hh, rows, H)]
         bias = (st[f"lstm.bias_ih_l{l}"] + st[f"lstm.bias_hh_l{l}"]).reshape(4, H).T.copy()       # [u][g]
-        bias *= -log2e
-        bias[:, 2] *= np.float32(2.0)
+        bias[:, [0, 1, 3]] *= np.float32(0.5)
         parts.append(np.ascontiguousarray(bias.reshape(-1), dtype=np.float32).view(np.uint8))
     return np.ascontiguousarray(np.concatenate(parts))
 

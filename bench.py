@@ -37,6 +37,7 @@ WORKLOADS = {
     "uarm_1024x100": (2, 1024, 100, 1),
     "pocket_1x100": (1, 1, 100, 1),
     "watch_only_1024x100": (0, 1024, 100, 1),
+    "pocket_1024x100": (1, 1024, 100, 1),
 }
 METRIC, UNIT = "mc_sampled_arm_pose_estimates_per_sec", "estimates/s"
 
