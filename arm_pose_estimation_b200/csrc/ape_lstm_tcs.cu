@@ -250,6 +250,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     for (int hp = 0; hp < 2 * NCH; ++hp) {
                         const int c = hp >> 1, half = hp & 1;
                         const uint32_t* r = rbuf[hp & 1];
+                        // this half-pass's bias (warp-uniform addresses, L1-resident) is requested before anything waits
+                        const float4* bias4 = reinterpret_cast<const float4*>(a.bias_s + (c * 32 + 8 * s + 4 * half) * 4);
+                        const float4 bsv[4] = {__ldg(bias4), __ldg(bias4 + 1), __ldg(bias4 + 2), __ldg(bias4 + 3)};
                         tmem_ld_wait();                        // this half-pass's columns have landed
                         if (a.trace && blockIdx.x == 0 && tile == cluster_id && warp == 0 && lane == 0 && (t == TRACE_T || t == TRACE_T - 1))
                             a.trace[512 + (t - TRACE_T + 1) * 16 + hp] = clock64();
@@ -267,7 +270,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                             }
                             tmem_ld_x16(tmem + t_lane + (uint32_t)((c1 & 1) * 128 + 32 * s + 16 * h1), rbuf[(hp + 1) & 1]);
                         }
-                        const float4* bias4 = reinterpret_cast<const float4*>(a.bias_s + (c * 32 + 8 * s + 4 * half) * 4);   // warp-uniform, L1-resident
                         // the 4 cells advance in lock-step through the transcendental stages (independent MUFU ops back to back):
                         //   e = 2^-(gate+bias)  ->  i*g~ and f share one reciprocal  ->  2^(-2c)  ->  h = o * tanh(c)
                         float hv[4], cn[4];
@@ -277,7 +279,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         float tg[16];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const float4 bs = __ldg(bias4 + u);    // 0.5 b (i, f, o), b (g)
+                            const float4 bs = bsv[u];              // 0.5 b (i, f, o), b (g)
                             tg[4 * u + 0] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 0]), 0.5f, bs.x));
                             tg[4 * u + 1] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 1]), 0.5f, bs.y));
                             tg[4 * u + 2] = tanh_approx(__uint_as_float(r[4 * u + 2]) + bs.z);
@@ -294,7 +296,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         float ev[16], num[4], den[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const float4 bs = __ldg(bias4 + u);    // 0.5 b (i, f, o), b (g) -> -log2e (gate + b), g: -2 log2e (gate + b)
+                            const float4 bs = bsv[u];              // 0.5 b (i, f, o), b (g) -> -log2e (gate + b), g: -2 log2e (gate + b)
                             ev[4 * u + 0] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 0]), -LOG2E, bs.x * (-2.0f * LOG2E)), EX2_CLAMP));
                             ev[4 * u + 1] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 1]), -LOG2E, bs.y * (-2.0f * LOG2E)), EX2_CLAMP));
                             ev[4 * u + 2] = ex2_approx(fminf(fmaf(__uint_as_float(r[4 * u + 2]), -2.0f * LOG2E, bs.z * (-2.0f * LOG2E)), EX2_CLAMP));

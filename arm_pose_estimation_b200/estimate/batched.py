@@ -102,7 +102,7 @@ class BatchedEstimator:
     def __init__(self, kind, layout, state, seq_len, y_targets, stats, n_streams, mc_samples,
                  smooth=1, dropout=0.2, bonemap=None, frames_per_call=1, emit_samples=True, normalize=True,
                  mask_mode=N.MASK_PHILOX, philox_seed=0, first_stream=0, device=None,
-                 lstm_variant="auto", tc_min_rows=4096, tc_tolerance_m=5e-5, pipeline=True):
+                 lstm_variant="auto", tc_min_rows=1, tc_tolerance_m=5e-5, pipeline=True):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedEstimator needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = N.load()
@@ -157,8 +157,9 @@ class BatchedEstimator:
             self.slot_event = [None, None]
             self.submits = 0
             # ---- which LSTM kernel: fp32 FFMA (exact) or tcgen05 fp16-operand tensor cores ----------------------
-            # Tensor cores only when the streams x MC-samples batch is a real dense contraction AND the fp16-operand
-            # result stays within tc_tolerance_m of the fp32 kernel on a probe batch of THIS model's weights.
+            # Tensor cores when the fp16-operand result stays within tc_tolerance_m of the fp32 kernel on a probe batch of
+            # THIS model's weights (and the batch has at least tc_min_rows rows: the measured crossover against the fp32
+            # kernel is below one row - profiles/r1_crossover.md - so the default does not restrict).
             self.tc_weights = None
             self.tc_probe_error_m = None
             self.lstm_variant = "fp32"

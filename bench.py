@@ -39,7 +39,19 @@ WORKLOADS = {
     "watch_only_1024x100": (0, 1024, 100, 1),
     "pocket_1024x100": (1, 1024, 100, 1),
 }
+WORKLOAD_TEXT = {
+    "uarm_1024x100": "watch+phone upper-arm estimator with quaternion FK, 1024 concurrent streams x 100 MC samples on 1 B200 (BASELINE configs[2])",
+    "pocket_1x100": "watch+phone pocket LSTM estimator, 1 stream x 100 MC samples (BASELINE configs[1])",
+    "watch_only_1024x100": "watch-only LSTM estimator (the model of BASELINE configs[0] / [3]), 1024 concurrent streams x 100 MC samples",
+    "pocket_1024x100": "watch+phone pocket LSTM estimator (the model of BASELINE configs[1]), 1024 concurrent streams x 100 MC samples",
+}
 METRIC, UNIT = "mc_sampled_arm_pose_estimates_per_sec", "estimates/s"
+
+
+def tc_kernel_name(H):
+    if H == 256:
+        return "lstm_layer_tcs_kernel<256> (one layer >= 1 launch; tcgen05 cta_group::2, fp16 operands, fp32 accumulate, TMA-streamed weights, h_t in TMEM)"
+    return f"lstm_layer_tc_kernel<{H}> (one layer >= 1 launch; tcgen05 cta_group::2, fp16 operands, fp32 accumulate, weights resident in shared memory)"
 
 
 def algorithmic_flops_per_estimate(I, H, L, T, O, n):
@@ -279,7 +291,7 @@ def run_ours(args, rank, world, local_rank):
     total_est = count * K * world
     tensor = be.lstm_variant == "tc"
     if tensor:
-        roofline = {"bound": "tensor", "kernel": "lstm_layer_tc_kernel<128> (one layer >= 1 launch; tcgen05 cta_group::2, fp16 operands, fp32 accumulate)",
+        roofline = {"bound": "tensor", "kernel": tc_kernel_name(H),
                     "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst) [{peak_src}]; fp16 and bf16 tcgen05.mma run at the same rate"}
     else:
@@ -294,7 +306,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": total_est / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": ("f16 operands, f32 accumulate/state" if tensor else "f32"), "data": "synthetic",
-        "config": {"workload": args.workload, "baseline_config": "watch+phone upper-arm estimator with quaternion FK, 1024 concurrent streams x 100 MC samples on 1 B200",
+        "config": {"workload": args.workload, "baseline_config": WORKLOAD_TEXT[args.workload],
                    "model": {"I": I, "H": H, "L": L, "T": T, "O": O, "dropout": spec["p"]}, "streams_per_gpu": count,
                    "mc_samples": n, "smooth": smooth, "frames_per_step": 1, "estimates_per_step_per_gpu": count,
                    "lstm_variant": ("tcgen05_fp16_operands_fp32_accumulate" if tensor else "fp32_ffma"),
@@ -307,6 +319,10 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline,
         "checksum": checksum,
     }
+    if rank == 0 and world == 1 and not args.no_other_models and args.workload == "uarm_1024x100":
+        del be                                                # free its buffers before the other models are set up
+        line["other_models"] = {w: quick_throughput(w, args.lstm, BatchedEstimator, N, syn, torch)
+                                for w in ("watch_only_1024x100", "pocket_1024x100")}
     if rank == 0 and world == 1 and not args.no_realtime:
         line["realtime"] = realtime_latency(BatchedEstimator, N, syn)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -322,6 +338,48 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def quick_throughput(workload, lstm, BatchedEstimator, N, syn, torch, steps=30, warmup=5):
+    """Device-resident throughput + roofline of the dominant kernel for the other two deployed models (both H = 256), same
+    shape as the headline workload: 1024 streams x 100 MC samples, one frame of every stream per step."""
+    from arm_pose_estimation_b200.estimate.batched import shard_streams
+    kind, B, n, smooth = WORKLOADS[workload]
+    spec = syn.kind_spec(kind)
+    I, H, L, T, O = (spec[k] for k in "IHLTO")
+    state = syn.synth_state_dict(I, H, L, O, 1234 + kind)
+    be = BatchedEstimator(kind=kind, layout=spec["layout"], state=state, seq_len=T, y_targets=spec["y_targets"], stats=spec["stats"],
+                          n_streams=B, mc_samples=n, smooth=smooth, dropout=spec["p"], frames_per_call=1, mask_mode=N.MASK_PHILOX,
+                          philox_seed=2026, emit_samples=True, lstm_variant=lstm)
+    base = syn.synth_rows(kind, 64, steps + warmup, config_id=3)
+    rows_dev = torch.from_numpy(np.ascontiguousarray(np.tile(base, (B // 64, 1, 1)))).cuda()
+    frames = [rows_dev[:, f:f + 1].contiguous() for f in range(steps + warmup)]
+    for f in range(warmup):
+        be.step_device(frames[f], raw_ready=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for f in range(warmup, warmup + steps):
+        be.step_device(frames[f], raw_ready=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    layer_ms, acc = np.zeros(L, np.float32), np.zeros(L, np.float64)
+    for f in range(5):
+        be.step_device(frames[warmup + f], layer_ms=layer_ms)
+        acc += layer_ms
+    torch.cuda.synchronize()
+    acc /= 5
+    peaks, _ = measured_peaks()
+    dom_ms = float(np.mean(acc[1:-1])) if L > 2 else float(acc[-1])
+    flops = B * n * T * 2 * 4 * H * (2 * H)
+    tensor = be.lstm_variant == "tc"
+    peak = peaks["bf16_tflops"] if tensor else 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
+    return {"config": WORKLOAD_TEXT[workload], "model": {"I": I, "H": H, "L": L, "T": T, "O": O}, "value": B * steps / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms / steps, "steps": steps, "lstm_variant": be.lstm_variant, "tc_probe_error_m": be.tc_probe_error_m,
+            "roofline": {"bound": "tensor" if tensor else "fp32_ffma", "kernel": tc_kernel_name(H) if tensor else "lstm_layer_fma_kernel",
+                         "achieved": flops / (dom_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / (dom_ms * 1e-3) / 1e12 / peak, "flops_per_launch": flops, "layer_ms": [float(v) for v in acc]}}
 
 
 def realtime_latency(BatchedEstimator, N, syn, frames=300):
@@ -356,6 +414,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=100, help="--impl reference: frames per worker per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-realtime", action="store_true", help="skip the configs[1] single-stream latency leg")
+    ap.add_argument("--no-other-models", action="store_true", help="skip the throughput legs of the two H = 256 models")
     ap.add_argument("--lstm", default="auto", choices=["auto", "fp32", "tc"], help="LSTM kernel variant (auto: probe-gated tensor cores)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))

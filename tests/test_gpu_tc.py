@@ -76,8 +76,10 @@ def test_tc_matches_fp32_kernel_on_many_tiles_with_philox():
 
 
 def test_auto_variant_selection():
-    small, _, _ = make(syn.KIND_UARM, 1, 100, "auto")                   # 100 rows: not a dense contraction -> fp32 FFMA
-    assert small.lstm_variant == "fp32"
+    small, _, _ = make(syn.KIND_UARM, 1, 100, "auto")                   # 100 rows: the tensor-core kernel still wins (profiles/r1_crossover.md)
+    assert small.lstm_variant == "tc"
+    gated, _, _ = make(syn.KIND_UARM, 1, 100, "auto", tc_min_rows=4096)  # a caller can still demand a minimum batch
+    assert gated.lstm_variant == "fp32"
     big, _, _ = make(syn.KIND_UARM, 256, 100, "auto")                   # 25600 rows -> tensor cores, if the probe passes
     assert big.lstm_variant == "tc" and big.tc_probe_error_m <= 5e-5
     wide, _, _ = make(syn.KIND_POCKET, 256, 100, "auto")                # H = 256: the streamed-weights tensor-core kernel
