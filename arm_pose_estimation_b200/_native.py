@@ -53,6 +53,7 @@ class LstmArgs(C.Structure):
         ("layer_begin", C.c_int), ("layer_end", C.c_int), ("ws_parity", C.c_int),
         ("trace", C.c_void_p),
         ("trace_layer", C.c_int),
+        ("stream_frames", C.c_void_p),
     ]
 
 
@@ -83,7 +84,7 @@ def load():
     lib.ape_lstm_blob_floats.restype = i32
     lib.ape_lstm_blob_floats.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_int64)]
     lib.ape_features.restype = i32
-    lib.ape_features.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp]
+    lib.ape_features.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, vp, i32, vp]
     lib.ape_mc_lstm_workspace_bytes.restype = i32
     lib.ape_mc_lstm_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(u64)]
     lib.ape_mc_lstm_fma.restype = i32
@@ -103,7 +104,7 @@ def load():
     lib.ape_mc_ff.restype = i32
     lib.ape_mc_ff.argtypes = [vp, i32, i32, i32, i32, f32, vp, i32, i32, i32, vp, u64, u32, u32, vp, vp]
     lib.ape_fk_reduce.restype = i32
-    lib.ape_fk_reduce.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.ape_fk_reduce.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.ape_msg_from_est.restype = i32
     lib.ape_msg_from_est.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp]
     # host self-check hooks: used by tests/ only

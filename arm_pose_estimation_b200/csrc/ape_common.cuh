@@ -22,6 +22,12 @@ inline int check_launch() {
     return e == cudaSuccess ? APE_OK : cuda_fail(e);
 }
 
+// ---- per-stream frame counters ----------------------------------------------------------------------
+// A launch either advances all streams in lock-step (frame0) or takes one absolute frame number per stream
+// (stream_frames[b]; a NEGATIVE entry means "this stream has no new frame in this call": its rows are still part of
+// the tiles, but nothing of it is written anywhere).
+APE_HD int stream_frame0(const int32_t* stream_frames, int frame0, int b) { return stream_frames ? stream_frames[b] : frame0; }
+
 // ---- quaternion algebra, [w,x,y,z], templated on the float type -----------------------------------
 template <typename F> struct Quat { F w, x, y, z; };
 template <typename F> struct Vec3 { F x, y, z; };

@@ -16,7 +16,7 @@ struct SmemRow {                       // indexable view of one staged row (odd 
 __global__ void __launch_bounds__(FEAT_ROWS_PER_CTA)
 features_kernel(const float* __restrict__ raw, int layout, int kind, const double* __restrict__ xx_m,
                 const double* __restrict__ xx_s, int normalize, float* __restrict__ feats,
-                int total_rows, int nF, int frame0, int feat_ring) {
+                int total_rows, int nF, int frame0, const int32_t* __restrict__ stream_frames, int feat_ring) {
     extern __shared__ float s_rows[];
     const int ncols = row_layout(layout).ncols;
     const int stride = ncols | 1;                                  // 29 / 55 words: odd
@@ -32,7 +32,10 @@ features_kernel(const float* __restrict__ raw, int layout, int kind, const doubl
     double xx[38];
     const int I = compute_features(kind, layout, SmemRow{s_rows + threadIdx.x * stride}, xx);
     const int row = row0 + threadIdx.x;
-    const int b = row / nF, f = frame0 + row % nF;
+    const int b = row / nF;
+    const int fb = stream_frames ? stream_frames[b] : frame0;       // per-stream frame counter; < 0: the stream sits this call out
+    if (fb < 0) return;
+    const int f = fb + row % nF;
     float* dst = feats + ((size_t)b * feat_ring + (f % feat_ring)) * I;
     for (int j = 0; j < I; ++j) {
         double v = normalize ? (xx[j] - xx_m[j]) / xx_s[j] : xx[j];   // estimator.py:103-104
@@ -43,7 +46,8 @@ features_kernel(const float* __restrict__ raw, int layout, int kind, const doubl
 }  // namespace ape
 
 extern "C" int ape_features(const float* raw, int layout, int kind, const double* xx_m, const double* xx_s,
-                            int normalize, float* feats, int B, int nF, int frame0, int feat_ring, void* stream) {
+                            int normalize, float* feats, int B, int nF, int frame0, const int32_t* stream_frames, int feat_ring,
+                            void* stream) {
     using namespace ape;
     if (!raw || !feats || B < 0 || nF < 0 || frame0 < 0 || feat_ring < 1) return APE_ERR_BAD_ARG;
     if (layout != APE_LAYOUT_WATCH_ONLY && layout != APE_LAYOUT_WATCH_PHONE) return APE_ERR_BAD_ARG;
@@ -58,6 +62,6 @@ extern "C" int ape_features(const float* raw, int layout, int kind, const double
     const size_t smem = (size_t)FEAT_ROWS_PER_CTA * stride * sizeof(float);
     const int grid = (int)((total + FEAT_ROWS_PER_CTA - 1) / FEAT_ROWS_PER_CTA);
     features_kernel<<<grid, FEAT_ROWS_PER_CTA, smem, (cudaStream_t)stream>>>(
-        raw, layout, kind, xx_m, xx_s, normalize, feats, (int)total, nF, frame0, feat_ring);
+        raw, layout, kind, xx_m, xx_s, normalize, feats, (int)total, nF, frame0, stream_frames, feat_ring);
     return check_launch();
 }

@@ -17,6 +17,7 @@ struct FkArgs {
     const float* yy_s;
     const float* body9;
     int O, B, nF, frame0, n, smooth;
+    const int32_t* stream_frames;   // per-stream frame counters (null: frame0 for all); < 0: skip the stream
     float* msg;
     float* samples;
     float* stdev;
@@ -66,7 +67,10 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32) fk_reduce_kernel(FkArgs
     const int e = blockIdx.x * FK_WARPS_PER_CTA + warp;
     const int E = a.B * a.nF;
     if (e >= E) return;
-    const int b = e / a.nF, f = a.frame0 + e % a.nF;
+    const int b = e / a.nF;
+    const int fb = a.stream_frames ? a.stream_frames[b] : a.frame0;
+    if (fb < 0) return;                            // the stream has no new frame in this call: its outputs stay untouched
+    const int f = fb + e % a.nF;
     const int S = a.smooth * a.n;
 
     Body<float> body;
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32) fk_reduce_kernel(FkArgs
 }  // namespace ape
 
 extern "C" int ape_fk_reduce(const float* preds, int pred_ring, const float* yy_m, const float* yy_s,
-                             const float* body9, int target, int O, int B, int nF, int frame0, int n_samples,
+                             const float* body9, int target, int O, int B, int nF, int frame0, const int32_t* stream_frames, int n_samples,
                              int smooth, float* msg, float* samples, float* stdev, float* est_rows,
                              int32_t* status, void* stream) {
     using namespace ape;
@@ -225,7 +229,7 @@ extern "C" int ape_fk_reduce(const float* preds, int pred_ring, const float* yy_
     const long long E = (long long)B * nF;
     if (E == 0) return APE_OK;
     if (E > 0x7fffffffLL || (long long)smooth * n_samples > 0x7fffffffLL) return APE_ERR_BAD_ARG;
-    FkArgs a{preds, pred_ring, yy_m, yy_s, body9, O, B, nF, frame0, n_samples, smooth, msg, samples, stdev, est_rows, status, nullptr};
+    FkArgs a{preds, pred_ring, yy_m, yy_s, body9, O, B, nF, frame0, n_samples, smooth, stream_frames, msg, samples, stdev, est_rows, status, nullptr};
     const int grid = (int)((E + FK_WARPS_PER_CTA - 1) / FK_WARPS_PER_CTA);
     cudaStream_t st = (cudaStream_t)stream;
     if (target == APE_TARGET_ORI_CAL_LARM_UARM)
@@ -244,7 +248,7 @@ extern "C" int ape_msg_from_est(const float* est, int W, const float* body9, int
     if (target < APE_TARGET_ORI_CAL_LARM_UARM || target > APE_TARGET_ORI_POS_CAL_LARM_UARM_HIPS) return APE_ERR_BAD_ARG;
     if (W != (target == APE_TARGET_ORI_CAL_LARM_UARM ? 14 : 21)) return APE_ERR_BAD_ARG;
     if (E == 0) return APE_OK;
-    FkArgs a{nullptr, 1, nullptr, nullptr, body9, target_num_outputs(target), E, 1, 0, S, 1, msg, nullptr, stdev, nullptr, nullptr, est};
+    FkArgs a{nullptr, 1, nullptr, nullptr, body9, target_num_outputs(target), E, 1, 0, S, 1, nullptr, msg, nullptr, stdev, nullptr, nullptr, est};
     const int grid = (E + FK_WARPS_PER_CTA - 1) / FK_WARPS_PER_CTA;
     cudaStream_t st = (cudaStream_t)stream;
     if (target == APE_TARGET_ORI_CAL_LARM_UARM)

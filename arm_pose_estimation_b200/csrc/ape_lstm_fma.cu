@@ -30,6 +30,7 @@ struct LayerArgs {
     const float* in;
     int in_R;                 // IN_SHARED: tile rows of the producing layer
     int feat_ring, nF, frame0;
+    const int32_t* stream_frames;   // per-stream frame counters (null: frame0 for all); < 0: the stream sits this call out
     int rows;                 // rows of this layer
     int n;                    // row -> estimate e = row / n, sample s = row % n
     int mask_mode;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerAr
                         v = __ldg(a.in + ((size_t)row * T + t) * a.Kin + k);
                     } else {                                           // sliding window, clamped at frame 0 (estimator.py:96-97)
                         const int b = row / a.nF;
-                        int fw = a.frame0 + row % a.nF - T + 1 + t;
+                        int fw = stream_frame0(a.stream_frames, a.frame0, b) + row % a.nF - T + 1 + t;
                         fw = fw < 0 ? 0 : fw;
                         v = __ldg(a.in + ((size_t)b * a.feat_ring + fw % a.feat_ring) * a.Kin + k);
                     }
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerAr
                             keep |= ((m.y >> (8 * j)) & 0xFFu ? 1u : 0u) << (4 + j);
                         }
                     } else if (a.mask_mode == APE_MASK_PHILOX) {
-                        const int b = e / a.nF, f = a.frame0 + e % a.nF;
+                        const int b = e / a.nF, f = stream_frame0(a.stream_frames, a.frame0, b) + e % a.nF;
                         keep = philox_keep8(a.seed, a.stream_id0 + (uint32_t)b, (uint32_t)f, (uint32_t)s, (uint32_t)a.gap,
                                             (uint32_t)t, (uint32_t)oct, a.keep_thr16);
                     }
@@ -261,7 +262,8 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerAr
                     a.preds[((size_t)row * T + t) * a.O + o] = sum;
                 } else {
                     const int e = row / a.n, s = row - e * a.n;
-                    const int b = e / a.nF, f = a.frame0 + e % a.nF;
+                    const int b = e / a.nF, fb = stream_frame0(a.stream_frames, a.frame0, b), f = fb + e % a.nF;
+                    if (fb < 0) continue;                              // inactive stream: keep its prediction ring untouched
                     float* dst = a.preds + (((size_t)b * a.pred_ring + f % a.pred_ring) * a.n_out) * a.O + o;
                     if (a.n == 1 && a.n_out > 1) {                     // single-layer model: no dropout, samples identical
                         for (int s2 = 0; s2 < a.n_out; ++s2) dst[(size_t)s2 * a.O] = sum;
@@ -371,7 +373,7 @@ int fma_launch_layer(const ape_lstm_args* g, int l, const FmaPlan& p, const floa
     a.Kin = l == 0 ? g->I : g->H;
     a.Kin_pad = ape_pack_kin_pad(l, g->I, g->H);
     a.H = g->H; a.T = g->T;
-    a.feat_ring = g->feat_ring; a.nF = g->nF; a.frame0 = g->frame0;
+    a.feat_ring = g->feat_ring; a.nF = g->nF; a.frame0 = g->frame0; a.stream_frames = g->stream_frames;
     a.mask_mode = l == 0 ? APE_MASK_NONE : g->mask_mode;
     a.masks = g->masks; a.gap = l - 1; a.n_gaps = g->L - 1;
     a.seed = g->philox_seed; a.stream_id0 = g->stream_id0;

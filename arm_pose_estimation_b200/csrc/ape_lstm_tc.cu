@@ -243,7 +243,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     epi_bar_sync();
                     if (valid) {
                         const int e = row / a.n, smp = row - e * a.n;
-                        const int b = e / a.nF, f = a.frame0 + e % a.nF;
+                        const int b = e / a.nF, fb = stream_frame0(a.stream_frames, a.frame0, b), f = fb + e % a.nF;
                         // this thread: outputs o = s, s+4, ... of its row (<= 5 for O <= 20), all accumulated in one sweep over k
                         // so every h value is read from shared memory once and the FMA chains are independent
                         float acc[5];
@@ -269,7 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 #pragma unroll
                         for (int i = 0; i < 5; ++i) {
                             const int o = s + 4 * i;
-                            if (o < a.O) {
+                            if (o < a.O && fb >= 0) {  // (an inactive stream keeps its prediction ring untouched)
                                 float* dst = a.preds + (((size_t)b * a.pred_ring + f % a.pred_ring) * a.n_out) * a.O + o;
                                 if (a.n == 1 && a.n_out > 1) for (int s2 = 0; s2 < a.n_out; ++s2) dst[(size_t)s2 * a.O] = acc[i];
                                 else dst[(size_t)smp * a.O] = acc[i];
@@ -291,7 +291,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
             const int row = (tile * 2 + (int)rank) * a.rpc + row_l;
             const bool valid = row_l < a.rpc && row < a.rows;
             const int e = valid ? row / a.n : 0, smp = valid ? row - e * a.n : 0;
-            const int b = e / a.nF, f = a.frame0 + e % a.nF;
+            const int b = e / a.nF, f = stream_frame0(a.stream_frames, a.frame0, b) + e % a.nF;
             for (int t = 0; t < T; ++t) {
                 if (a.in_mode == IN_UNITS || a.in_mode == IN_SHARED_UNITS) {
                     // all loads of the step go out before anything waits; masks are ANDed in as the data lands; only the
@@ -528,7 +528,7 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
         a.T = g->T;
         a.kgx = tc_kgx(l, g->I, H);
         a.Kin = l == 0 ? g->I : H;
-        a.feat_ring = g->feat_ring; a.nF = g->nF; a.frame0 = g->frame0;
+        a.feat_ring = g->feat_ring; a.nF = g->nF; a.frame0 = g->frame0; a.stream_frames = g->stream_frames;
         if (l == 0) {
             a.in_mode = g->x_dense ? tc::IN_DENSE_F32 : tc::IN_WINDOW_F32;
             a.in = g->x_dense ? (const void*)g->x_dense : (const void*)g->feat_ring_buf;

@@ -22,6 +22,7 @@ struct TcLayerArgs {
     int in_mode;
     const void* in;
     int feat_ring, nF, frame0, rows, n;
+    const int32_t* stream_frames;   // per-stream frame counters (null: frame0 for all); < 0: the stream sits this call out
     int mask_mode;
     const uint8_t* masks;
     int gap, n_gaps;

@@ -367,11 +367,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         }
                         if (valid) {
                             const int e = row / a.n, smp = row - e * a.n;
-                            const int b = e / a.nF, f = a.frame0 + e % a.nF;
+                            const int b = e / a.nF, fb = stream_frame0(a.stream_frames, a.frame0, b), f = fb + e % a.nF;
 #pragma unroll
                             for (int i = 0; i < 5; ++i) {
                                 const int o = s + 4 * i;
-                                if (o < a.O) {
+                                if (o < a.O && fb >= 0) {  // (an inactive stream keeps its prediction ring untouched)
                                     float* dst = a.preds + (((size_t)b * a.pred_ring + f % a.pred_ring) * a.n_out) * a.O + o;
                                     if (a.n == 1 && a.n_out > 1) for (int s2 = 0; s2 < a.n_out; ++s2) dst[(size_t)s2 * a.O] = acc[i];
                                     else dst[(size_t)smp * a.O] = acc[i];
@@ -392,7 +392,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
             const int row = (tile * 2 + (int)rank) * a.rpc + row_l;
             const bool valid = row_l < a.rpc && row < a.rows;
             const int e = valid ? row / a.n : 0, smp = valid ? row - e * a.n : 0;
-            const int b = e / a.nF, f = a.frame0 + e % a.nF;
+            const int b = e / a.nF, f = stream_frame0(a.stream_frames, a.frame0, b) + e % a.nF;
             for (int t = 0; t < T; ++t, ++gl) {
                 uint8_t* sX = sAx + (gl & 1) * C::A_BYTES;
                 // the tile written two steps ago has been consumed (the loader may run up to two steps ahead of the MMAs)

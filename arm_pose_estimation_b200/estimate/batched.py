@@ -155,6 +155,7 @@ class BatchedEstimator:
             self.raw_host = [torch.zeros((B, nF, self.ncols), dtype=f32).pin_memory() for _ in range(2)]
             self.out_host = [torch.zeros(n_words, dtype=f32).pin_memory() for _ in range(2)]
             self.slot_event = [None, None]
+            self.frames_host = self.frames_dev = None      # per-stream frame counters (multi-stream front-end), made on first use
             self.submits = 0
             # ---- which LSTM kernel: fp32 FFMA (exact) or tcgen05 fp16-operand tensor cores ----------------------
             # Tensor cores when the fp16-operand result stays within tc_tolerance_m of the fp32 kernel on a probe batch of
@@ -214,7 +215,7 @@ class BatchedEstimator:
             est = torch.empty((n_est, n_samples, EST_WIDTH[self.target]), dtype=torch.float32, device=dev)
             msg = torch.empty((n_est, 25), dtype=torch.float32, device=dev)
             N.check(self.lib.ape_fk_reduce(N.ptr(preds), 1, N.ptr(self.yy_m), N.ptr(self.yy_s), N.ptr(self.body), self.target,
-                                           self.O, n_est, 1, 0, n_samples, 1, N.ptr(msg), None, None, N.ptr(est), None,
+                                           self.O, n_est, 1, 0, None, n_samples, 1, N.ptr(msg), None, None, N.ptr(est), None,
                                            N.current_stream_ptr()), "ape_fk_reduce (probe)")
             outs.append(est[..., :9 if EST_WIDTH[self.target] == 21 else 6].clone())
         torch.cuda.current_stream().synchronize()
@@ -235,11 +236,13 @@ class BatchedEstimator:
 
     # ---- device path -----------------------------------------------------------------------------------
     def step_device(self, raw, n_frames=None, masks=None, layer_ms=None, trace=None, trace_layer=1, raw_ready=False,
-                    _h2d_from=None):
+                    _h2d_from=None, stream_frames=None, _frames_from=None):
         """``raw``: device tensor ``[B, nF, ncols]`` float32 (nF <= frames_per_call).  Enqueues the three stages and returns an
         ``EstimateBatch`` of views into the estimator's device buffers (valid until the call after next).  ``raw_ready=True``
         promises that ``raw`` is already materialised (not pending on the current stream), which lets the pipelined path
-        start stage 1 + layer 0 of this call under the previous call's kernels."""
+        start stage 1 + layer 0 of this call under the previous call's kernels.  ``stream_frames``: optional device int32
+        tensor ``[B]`` of per-stream absolute frame numbers for streams that do not advance in lock-step (a negative entry
+        skips the stream in this call: its rings and outputs stay untouched); the shared frame counter is then not used."""
         nF = int(raw.shape[1]) if n_frames is None else int(n_frames)
         if raw.shape[0] != self.B or nF > self.nF_max or raw.shape[2] != self.ncols or not raw.is_contiguous():
             raise UserWarning(f"raw rows must be a contiguous [B={self.B}, nF<={self.nF_max}, {self.ncols}] tensor, got {tuple(raw.shape)}")
@@ -252,7 +255,11 @@ class BatchedEstimator:
         a.I, a.H, a.L, a.T, a.O = self.I, self.H, self.L, self.T, self.O
         a.dropout_p = self.p
         a.x_dense, a.feat_ring_buf, a.feat_ring = None, self.feats.data_ptr(), self.feat_ring
-        a.B, a.nF, a.frame0, a.n_samples = B, nF, self.frame, self.n
+        frame0, sf = (self.frame, None) if stream_frames is None else (0, stream_frames)
+        if sf is not None and (sf.dtype != torch.int32 or sf.numel() != B or not sf.is_cuda):
+            raise UserWarning("stream_frames must be a device int32 tensor of B entries")
+        a.B, a.nF, a.frame0, a.n_samples = B, nF, frame0, self.n
+        a.stream_frames = None if sf is None else sf.data_ptr()
         a.mask_mode = self.mask_mode if self.L > 1 else N.MASK_NONE
         md = None
         if a.mask_mode == N.MASK_INJECTED:
@@ -273,7 +280,7 @@ class BatchedEstimator:
 
         def features(stream_ptr):
             N.check(lib.ape_features(N.ptr(raw), self.layout, self.kind, N.ptr(self.xx_m), N.ptr(self.xx_s),
-                                     1 if self.normalize else 0, N.ptr(self.feats), B, nF, self.frame, self.feat_ring, stream_ptr),
+                                     1 if self.normalize else 0, N.ptr(self.feats), B, nF, frame0, N.ptr(sf), self.feat_ring, stream_ptr),
                     "ape_features")
 
         if self.pipeline and layer_ms is None and trace is None:
@@ -287,6 +294,8 @@ class BatchedEstimator:
             with torch.cuda.stream(side):
                 if _h2d_from is not None:
                     raw.copy_(_h2d_from, non_blocking=True)
+                if _frames_from is not None:
+                    sf.copy_(_frames_from, non_blocking=True)
                 sp = C_void(side.cuda_stream)
                 features(sp)
                 a.layer_begin, a.layer_end, a.ws_parity = 0, 1, parity
@@ -303,11 +312,13 @@ class BatchedEstimator:
         else:
             if _h2d_from is not None:
                 raw.copy_(_h2d_from, non_blocking=True)
+            if _frames_from is not None:
+                sf.copy_(_frames_from, non_blocking=True)
             st = N.current_stream_ptr()
             features(st)
             N.check(self._lstm_fn()(a, st), "ape_mc_lstm")
         N.check(lib.ape_fk_reduce(N.ptr(self.preds), self.pred_ring, N.ptr(self.yy_m), N.ptr(self.yy_s), N.ptr(self.body),
-                                  self.target, self.O, B, nF, self.frame, self.n, self.smooth,
+                                  self.target, self.O, B, nF, frame0, N.ptr(sf), self.n, self.smooth,
                                   N.ptr(self.msg), N.ptr(self.samples), N.ptr(self.std), None, N.ptr(self.status), st),
                 "ape_fk_reduce")
         self.launches += 2 + self.L
@@ -325,10 +336,11 @@ class BatchedEstimator:
         return buf.reshape(-1)[: self.B * nF * int(np.prod(tail, dtype=np.int64))].view(self.B, nF, *tail)
 
     # ---- host-facing path: pinned H2D, the three stages, pinned D2H ------------------------------------------
-    def submit(self, rows, masks=None):
+    def submit(self, rows, masks=None, stream_frames=None):
         """Stage ``rows`` (host array ``[B, nF, ncols]`` or ``[B, ncols]`` of float32 wire rows) in pinned memory and
         enqueue H2D copy -> the three stages -> D2H copy on the current stream WITHOUT waiting.  Returns a
-        ``PendingEstimate``; at most two may be outstanding (two staging slots)."""
+        ``PendingEstimate``; at most two may be outstanding (two staging slots).  ``stream_frames``: optional host int32
+        array ``[B]`` of per-stream frame numbers (negative: the stream has no new row in this call), see ``step_device``."""
         rows = np.asarray(rows, dtype=np.float32)
         if rows.ndim == 2:
             rows = rows[:, None, :]
@@ -348,7 +360,14 @@ class BatchedEstimator:
             self._use_out(slot)
             if self.copy_done[slot] is not None:
                 main.wait_event(self.copy_done[slot])     # device buffer `slot` has been read back (call k-2)
-            out = self.step_device(raw, nF, masks, _h2d_from=stage)
+            sf_dev = sf_host = None
+            if stream_frames is not None:
+                if self.frames_host is None:
+                    self.frames_host = [torch.zeros(self.B, dtype=torch.int32).pin_memory() for _ in range(2)]
+                    self.frames_dev = [torch.zeros(self.B, dtype=torch.int32, device=self.device) for _ in range(2)]
+                sf_host, sf_dev = self.frames_host[slot], self.frames_dev[slot]
+                sf_host.numpy()[...] = np.asarray(stream_frames, dtype=np.int32).reshape(self.B)
+            out = self.step_device(raw, nF, masks, _h2d_from=stage, stream_frames=sf_dev, _frames_from=sf_host)
             computed = torch.cuda.Event()
             computed.record(main)
             host, dev_out = self.out_host[slot], self.out_all
@@ -374,10 +393,10 @@ class BatchedEstimator:
         samples = host[Em * 32: Em * 32 + E * self.S * 6].reshape(self.B, nF, self.S, 6) if self.emit_samples else None
         return msg, std, samples, status
 
-    def step(self, rows, masks=None):
+    def step(self, rows, masks=None, stream_frames=None):
         """``submit`` + wait.  Returns an ``EstimateBatch`` of HOST arrays (views of a pinned staging slot, valid until
         the slot is reused two calls later)."""
-        return self.submit(rows, masks).result()
+        return self.submit(rows, masks, stream_frames).result()
 
     @property
     def h2d_bytes_per_frame(self):

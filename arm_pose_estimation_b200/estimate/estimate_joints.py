@@ -37,7 +37,7 @@ def fk_rows(preds, body_measurements, y_targets, want_msg=False):
     msg = torch.empty(25, dtype=torch.float32, device="cuda")
     std = torch.empty(6, dtype=torch.float32, device="cuda")
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
-    N.check(N.load().ape_fk_reduce(N.ptr(p), 1, None, None, N.ptr(body), target, O, 1, 1, 0, S, 1,
+    N.check(N.load().ape_fk_reduce(N.ptr(p), 1, None, None, N.ptr(body), target, O, 1, 1, 0, None, S, 1,
                                    N.ptr(msg), None, N.ptr(std), N.ptr(est), N.ptr(status), N.current_stream_ptr()),
             "ape_fk_reduce")
     if int(status.item()) != 0:

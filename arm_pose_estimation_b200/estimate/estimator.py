@@ -250,7 +250,7 @@ class _NNEstimator(Estimator):
         raw = torch.from_numpy(np.ascontiguousarray(r[:ncols])).cuda()
         I = len(self._x_inputs.value)
         out = torch.empty(I, dtype=torch.float32, device="cuda")
-        N.check(N.load().ape_features(N.ptr(raw), self._layout, self._kind, None, None, 0, N.ptr(out), 1, 1, 0, 1,
+        N.check(N.load().ape_features(N.ptr(raw), self._layout, self._kind, None, None, 0, N.ptr(out), 1, 1, 0, None, 1,
                                       N.current_stream_ptr()), "ape_features")
         return out.cpu().numpy().astype(self._xx_dtype)
 

@@ -13,6 +13,11 @@
  * f = frame0 + f_rel.  Frame-indexed device buffers are rings of `*_ring` frames per stream, slot
  * f % ring; frames before 0 clamp to frame 0, which reproduces the reference's "repeat the first
  * row / first prediction" warm-up (estimator.py:96-97, :114-115).
+ *
+ * Streams that do not advance in lock-step (many sockets feeding one GPU, each with the reference's
+ * "drop the backlog" freshness policy, estimator.py:159-161): every stage takes an optional device array
+ * `stream_frames[B]` of per-stream absolute frame numbers that replaces frame0; a NEGATIVE entry means
+ * "no new frame for this stream in this call" - the stream's rings and outputs are left untouched.
  */
 #ifndef APE_B200_H
 #define APE_B200_H
@@ -70,7 +75,8 @@ int ape_lstm_blob_floats(int I, int H, int L, int O, int64_t* floats);
  * Arithmetic is float64 with the reference's float32 rounding point (watch_only.py:82) kept.
  */
 int ape_features(const float* raw, int layout, int kind, const double* xx_m, const double* xx_s,
-                 int normalize, float* feats, int B, int nF, int frame0, int feat_ring, void* stream);
+                 int normalize, float* feats, int B, int nF, int frame0, const int32_t* stream_frames,
+                 int feat_ring, void* stream);
 
 /* ---- stage 2: MC-dropout LSTM regressor -------------------------------------------------------- */
 /*
@@ -115,6 +121,8 @@ typedef struct ape_lstm_args {
        tile of CTA 0 of layer `trace_layer` ([role: epilogue, loader, issuer][step < 16][event < 16]) */
     void* trace;
     int trace_layer;
+    /* per-stream frame counters [B] on the device (null: every stream is at frame0); < 0: skip the stream */
+    const int32_t* stream_frames;
 } ape_lstm_args;
 
 int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
@@ -167,7 +175,7 @@ int ape_mc_ff(const float* blob, int I, int H, int Lh, int O, float dropout_p, c
  *   status   [E] int32 or null: 0 ok, 1 = a 6D pair was degenerate (the reference raises LinAlgError)
  */
 int ape_fk_reduce(const float* preds, int pred_ring, const float* yy_m, const float* yy_s, const float* body9,
-                  int target, int O, int B, int nF, int frame0, int n_samples, int smooth,
+                  int target, int O, int B, int nF, int frame0, const int32_t* stream_frames, int n_samples, int smooth,
                   float* msg, float* samples, float* stdev, float* est_rows, int32_t* status, void* stream);
 
 /*

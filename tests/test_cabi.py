@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = N.load()
     for name in declared_symbols():
         assert getattr(lib, name) is not None, name
-    assert lib.ape_abi_version() == 3
+    assert lib.ape_abi_version() == 4
 
 
 def test_struct_layout_matches_header():
@@ -60,9 +60,9 @@ def test_blob_size_mirror():
 
 def test_bad_arguments_are_refused():
     lib = N.load()
-    assert lib.ape_features(None, 0, 0, None, None, 0, None, 1, 1, 0, 1, None) == N.APE_ERR_BAD_ARG
+    assert lib.ape_features(None, 0, 0, None, None, 0, None, 1, 1, 0, None, 1, None) == N.APE_ERR_BAD_ARG
     assert lib.ape_mc_lstm_fma(None, None) == N.APE_ERR_BAD_ARG
-    assert lib.ape_fk_reduce(None, 1, None, None, None, 0, 12, 1, 1, 0, 1, 1, None, None, None, None, None, None) == N.APE_ERR_BAD_ARG
+    assert lib.ape_fk_reduce(None, 1, None, None, None, 0, 12, 1, 1, 0, None, 1, 1, None, None, None, None, None, None) == N.APE_ERR_BAD_ARG
     out = ctypes.c_uint64(0)
     assert lib.ape_mc_lstm_workspace_bytes(38, 100, 3, 6, 12, 4, 10, ctypes.byref(out)) == N.APE_ERR_UNSUPPORTED   # H % 32 != 0
     assert lib.ape_mc_lstm_workspace_bytes(38, 128, 3, 6, 12, 1024, 100, ctypes.byref(out)) == N.APE_OK and out.value > 0
