@@ -158,3 +158,59 @@ def test_tc256_repeated_runs_are_bit_identical():
         else:
             np.testing.assert_array_equal(out.msg, ref_msg)
             np.testing.assert_array_equal(out.samples, ref_smp)
+
+
+# ---- odd shapes through the C ABI: both tensor-core kernels against the oracle's decomposed LSTM with injected masks ------------
+
+def _lstm_last_step(state, dims, x, n, masks, variant, p):
+    """ape_mc_lstm_{fma,tc} on dense windows x [E, T, I] -> preds [E, n, O] (last step), injected masks [E, L-1, T, n, H]."""
+    I, H, L, T, O = dims
+    E = x.shape[0]
+    lib = N.load()
+    w32 = torch.from_numpy(batched.nn_models.pack_lstm_weights(state)).cuda()
+    wtc = torch.from_numpy(batched.nn_models.pack_lstm_weights_tc(state)).cuda()
+    xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).cuda()
+    md = torch.from_numpy(np.ascontiguousarray(masks, dtype=np.uint8)).cuda()
+    ws = torch.empty(N.workspace_bytes(I, H, L, T, O, E, n, tensor_core=(variant == "tc")) + 4096, dtype=torch.uint8, device="cuda")
+    preds = torch.full((E, 1, n, O), float("nan"), dtype=torch.float32, device="cuda")
+    a = N.LstmArgs()
+    a.weights, a.weights_tc = w32.data_ptr(), wtc.data_ptr()
+    a.I, a.H, a.L, a.T, a.O = I, H, L, T, O
+    a.dropout_p = p
+    a.x_dense, a.feat_ring_buf, a.feat_ring = xd.data_ptr(), None, 0
+    a.B, a.nF, a.frame0, a.n_samples = E, 1, 0, n
+    a.mask_mode, a.masks = N.MASK_INJECTED, md.data_ptr()
+    a.workspace = ws.data_ptr()
+    a.preds, a.pred_ring, a.all_steps = preds.data_ptr(), 1, 0
+    N.check((lib.ape_mc_lstm_tc if variant == "tc" else lib.ape_mc_lstm_fma)(a, N.current_stream_ptr()), variant)
+    torch.cuda.synchronize()
+    return preds.cpu().numpy()[:, 0]
+
+
+@pytest.mark.parametrize("I,H,L,T,O,E,n", [
+    (20, 256, 3, 3, 20, 3, 100),      # H = 256 with a middle layer (inter-layer units through HBM), odd T, widest output layer, ragged tile
+    (38, 256, 2, 1, 12, 2, 130),      # a single step: no recurrent half at all; x-part of 6 k-groups
+    (7, 256, 2, 5, 14, 300, 1),       # one sample per estimate, 300 rows: layer 0 and layer 1 tiles of different shapes
+    (38, 128, 4, 7, 13, 5, 60),       # H = 128, two middle layers, odd T, odd O
+    (12, 64, 2, 2, 1, 1, 1),          # the smallest everything
+])
+def test_tc_odd_shapes_against_oracle(I, H, L, T, O, E, n):
+    from oracle import lstm as OL
+    p = 0.25
+    state = syn.synth_state_dict(I, H, L, O, 31 + H + L)
+    rng = np.random.default_rng(I * 7 + T)
+    x = rng.normal(size=(E, T, I)).astype(np.float32)
+    masks = (rng.random(size=(E, L - 1, T, n, H)) < 1 - p).astype(np.uint8)
+    got_tc = _lstm_last_step(state, (I, H, L, T, O), x, n, masks, "tc", p)
+    got_32 = _lstm_last_step(state, (I, H, L, T, O), x, n, masks, "fp32", p)
+    assert np.isfinite(got_tc).all()
+    worst_32 = worst_tc = 0.0
+    for e in range(min(E, 4)):
+        want = OL.forward_with_masks(state, np.repeat(x[e:e + 1], n, 0), list(masks[e]), p)[:, -1, :]
+        worst_32 = max(worst_32, float(np.abs(got_32[e] - want).max()))
+        worst_tc = max(worst_tc, float(np.abs(got_tc[e] - want).max()))
+    scale = float(np.abs(got_32).max())
+    print(f"I{I} H{H} L{L} T{T} O{O} E{E} n{n}: fp32 kernel {worst_32:.3g}, tensor-core kernel {worst_tc:.3g} (|pred| <= {scale:.3g}); "
+          f"tc vs fp32 over all rows {np.abs(got_tc - got_32).max():.3g}")
+    assert worst_32 <= 2e-5
+    assert worst_tc <= 2e-4 and np.abs(got_tc - got_32).max() <= 2e-4        # fp16 operands (measured <= 9e-6 on |pred| ~ 0.08)
