@@ -41,11 +41,12 @@ using tc::EX2_CLAMP;
 
 using tc::tanh_approx;
 
-constexpr int EPI_WARPS = 16, LOAD_WARPS = 8;
+constexpr int EPI_WARPS = 16, LOAD_WARPS = 4;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS;   // leader CTA: MMA issuer; peer CTA: forwards "piece landed" to the leader
-constexpr int TMA_WARP = MMA_WARP + 1;             // one lane per CTA fills the weight ring
-constexpr int THREADS = (TMA_WARP + 1) * 32;       // 832
+constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS;   // leader CTA: MMA issuers (MMA_WARP + k issues the chunks of accumulator slot k);
+constexpr int N_ISSUERS = 2;                       //   peer CTA: the first of them forwards "piece landed" to the leader
+constexpr int TMA_WARP = MMA_WARP + N_ISSUERS;     // one lane per CTA fills the weight ring
+constexpr int THREADS = (TMA_WARP + 1) * 32;       // 736: 88 registers per thread
 constexpr int ROWS = 128;                          // rows per CTA = TMEM lanes
 constexpr int NSLOT = 2;                           // accumulator slots of 128 TMEM columns
 constexpr int SLICE_KG = 4;                        // k-groups (of 8 K-values) per published K-slice of h_t (one chunk's 32 units)
@@ -55,6 +56,14 @@ constexpr uint32_t KG_BYTES_B = 64 * 16;           // one k-group of a 64-column
 constexpr uint32_t SLOT_BYTES = SLOT_KG * KG_BYTES_B;    // ring slot = 16 KB
 constexpr uint32_t BAR_BLOCK_BYTES = 512;
 constexpr uint32_t SMEM_LIMIT = 227 * 1024;
+#ifndef APE_TCS_TRACE
+#define APE_TCS_TRACE 0      // 1: the issuer / producer loops stamp SM clocks into args.trace (tools/tcs_trace.py); costs issue time
+#endif
+#if APE_TCS_TRACE
+#define TCS_TR(...) __VA_ARGS__
+#else
+#define TCS_TR(...)
+#endif
 constexpr int TRACE_T = 3;                         // tracing (args.trace): the step of the first tile of CTA 0 that is stamped
 
 template <int H> struct Cfg {
@@ -63,18 +72,21 @@ template <int H> struct Cfg {
     static constexpr uint32_t FIXED = 2 * A_BYTES + BAR_BLOCK_BYTES;
     static constexpr int NP = (SMEM_LIMIT - FIXED) / SLOT_BYTES;      // ring depth (slots)
     static constexpr uint32_t SMEM = FIXED + NP * SLOT_BYTES;
+    // "piece landed" barriers are indexed by the piece's sequence number (a piece may span two slots): at most NP pieces are
+    // in flight, so NFULL > NP barriers never alias
+    static constexpr int NFULL = 8;
     static constexpr uint32_t H_COL = NSLOT * 128;                    // first TMEM column of the two h buffers
     static constexpr uint32_t H_COLS = H / 2;                         // fp16 pairs: one buffer
     static constexpr uint32_t TMEM_COLS = 512;
     static constexpr size_t CSTATE_BYTES = (size_t)H * ROWS * 4;      // per-CTA cell-state scratch (global, L2-resident)
     enum {
         BAR_X_READY = 0, BAR_X_DONE = 2, BAR_ACC_READY = 4, BAR_SLOT_FREE = BAR_ACC_READY + NSLOT,
-        BAR_H_READY = BAR_SLOT_FREE + NSLOT, BAR_W_FULL = BAR_H_READY + NCH, BAR_W_EMPTY = BAR_W_FULL + NP,
+        BAR_H_READY = BAR_SLOT_FREE + NSLOT, BAR_W_FULL = BAR_H_READY + NCH, BAR_W_EMPTY = BAR_W_FULL + NFULL,
         BAR_COUNT = BAR_W_EMPTY + NP
     };
     static_assert(NSLOT == 2 && NCH % 2 == 0 && NCH > NSLOT, "chunks alternate between the two accumulator slots");
     static_assert(H_COL + 2 * H_COLS <= TMEM_COLS, "accumulator slots + two h buffers must fit the 512 TMEM columns");
-    static_assert(NP >= 3 && NP <= 16, "weight ring depth");
+    static_assert(NP >= 3 && NP < NFULL, "weight ring depth");
     static_assert(BAR_COUNT * 8 + 16 <= BAR_BLOCK_BYTES, "barrier block too small");
 };
 
@@ -82,7 +94,7 @@ template <int H> struct Cfg {
 //   chunk_begin(c)                      slot c & 1 is about to be refilled
 //   piece(c, is_h, kg0, nkg, first)     chunk c (+)= A[:, k-groups kg0 .. kg0+nkg) x W_c[k-groups]^T  (x-part or recurrent part);
 //                                       a recurrent piece needs the K-slices (of SLICE_KG k-groups) it covers published
-//   acc_done(c) / x_done()              chunk c complete / the x tile has been consumed
+//   acc_done(c) / x_done()              chunk c complete / this slot's share of the x tile has been consumed
 template <int NCH, class V>
 static void walk_step(bool first_step, int kgx, V& v) {
     const int KG = NCH * SLICE_KG;
@@ -93,7 +105,7 @@ static void walk_step(bool first_step, int kgx, V& v) {
     for (int c = 0; c < NCH; ++c) {
         v.chunk_begin(c);
         range(c, false, 0, kgx, true);
-        if (c == NCH - 1) v.x_done();
+        if (c >= NCH - NSLOT) v.x_done();                      // the last x-part of each accumulator slot (= of each issuer)
         if (first_step) {                                      // h_{-1} = 0: no recurrent half
             v.acc_done(c);
         } else if (c >= NSLOT) {                               // refilled inside the step: all of h_{t-1} is there
@@ -185,18 +197,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars[C::BAR_X_READY + b], 2 * LOAD_WARPS);
-            mbar_init(&bars[C::BAR_X_DONE + b], 1);
+            mbar_init(&bars[C::BAR_X_DONE + b], N_ISSUERS);    // each issuer commits after ITS last x-part of the step
         }
         for (int s = 0; s < NSLOT; ++s) {
             mbar_init(&bars[C::BAR_ACC_READY + s], 1);
             mbar_init(&bars[C::BAR_SLOT_FREE + s], 2 * EPI_WARPS);
         }
         for (int c = 0; c < NCH; ++c) mbar_init(&bars[C::BAR_H_READY + c], 2 * EPI_WARPS);
-        for (int p = 0; p < NP; ++p) {
-            // leader: its own copy (arrive.expect_tx + bytes) and the peer's "my copy landed" arrival; peer: its own copy
-            mbar_init(&bars[C::BAR_W_FULL + p], rank == 0 ? 2 : 1);
-            mbar_init(&bars[C::BAR_W_EMPTY + p], 1);
-        }
+        // leader: its own copy (arrive.expect_tx + bytes) and the peer's "my copy landed" arrival; peer: its own copy
+        for (int p = 0; p < C::NFULL; ++p) mbar_init(&bars[C::BAR_W_FULL + p], rank == 0 ? 2 : 1);
+        for (int p = 0; p < NP; ++p) mbar_init(&bars[C::BAR_W_EMPTY + p], 1);
         mbar_init_fence();
     }
     fence_proxy_async_smem();
@@ -239,6 +249,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     // the loads of half-pass hp+1 are in flight while the cells of half-pass hp are computed.
                     uint32_t rbuf[2][16];
                     float4 cbuf[2];
+                    bool prefetched = true;
                     float hlo[4];
                     cbuf[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     cbuf[1] = cbuf[0];
@@ -253,6 +264,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         // this half-pass's bias (warp-uniform addresses, L1-resident) is requested before anything waits
                         const float4* bias4 = reinterpret_cast<const float4*>(a.bias_s + (c * 32 + 8 * s + 4 * half) * 4);
                         const float4 bsv[4] = {__ldg(bias4), __ldg(bias4 + 1), __ldg(bias4 + 2), __ldg(bias4 + 3)};
+                        if (half == 0 && hp > 0 && !prefetched) {      // the chunk was not complete yet when the last half-pass looked
+                            mbar_wait_wd(&bars[C::BAR_ACC_READY + (c & 1)], par0 ^ ((c >> 1) & 1));
+                            fence_after_sync();
+                            tmem_ld_x16(tmem + t_lane + (uint32_t)((c & 1) * 128 + 32 * s), rbuf[hp & 1]);
+                        }
                         tmem_ld_wait();                        // this half-pass's columns have landed
                         if (a.trace && blockIdx.x == 0 && tile == cluster_id && warp == 0 && lane == 0 && (t == TRACE_T || t == TRACE_T - 1))
                             a.trace[512 + (t - TRACE_T + 1) * 16 + hp] = clock64();
@@ -264,11 +280,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         if (hp + 1 < 2 * NCH) {
                             const int c1 = (hp + 1) >> 1, h1 = (hp + 1) & 1;
                             if (t > 0) cbuf[(hp + 1) & 1] = __ldcg(cst + (size_t)((4 * c1 + s) * 2 + h1) * ROWS);
+                            // Next chunk: its accumulators are prefetched under this half-pass IF the chunk is already complete -
+                            // waiting for it here would tie the pass period to the refill latency of the two-slot ring (drain of
+                            // chunk c -> chunk c+2 complete), so an unfinished chunk is waited for at the top of its own pass.
+                            prefetched = true;
                             if (half == 1) {
-                                mbar_wait_wd(&bars[C::BAR_ACC_READY + (c1 & 1)], par0 ^ ((c1 >> 1) & 1));
-                                fence_after_sync();
+                                prefetched = __all_sync(0xffffffffu, mbar_test_wait_addr(smem_u32(&bars[C::BAR_ACC_READY + (c1 & 1)]), par0 ^ ((c1 >> 1) & 1)));
+                                if (prefetched) fence_after_sync();
                             }
-                            tmem_ld_x16(tmem + t_lane + (uint32_t)((c1 & 1) * 128 + 32 * s + 16 * h1), rbuf[(hp + 1) & 1]);
+                            if (prefetched) tmem_ld_x16(tmem + t_lane + (uint32_t)((c1 & 1) * 128 + 32 * s + 16 * h1), rbuf[(hp + 1) & 1]);
                         }
                         // the 4 cells advance in lock-step through the transcendental stages (independent MUFU ops back to back):
                         //   e = 2^-(gate+bias)  ->  i*g~ and f share one reciprocal  ->  2^(-2c)  ->  h = o * tanh(c)
@@ -280,6 +300,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const float4 bs = bsv[u];              // 0.5 b (i, f, o), b (g)
+#if APE_EXP == 7      // timing experiment: half of the epilogue warps skip the MUFU work (results wrong) - is the cell phase XU-contention bound?
+                            if (s & 1) {
+                                tg[4 * u + 0] = fmaf(__uint_as_float(r[4 * u + 0]), 0.5f, bs.x) * 0.1f;
+                                tg[4 * u + 1] = fmaf(__uint_as_float(r[4 * u + 1]), 0.5f, bs.y) * 0.1f;
+                                tg[4 * u + 2] = (__uint_as_float(r[4 * u + 2]) + bs.z) * 0.1f;
+                                tg[4 * u + 3] = fmaf(__uint_as_float(r[4 * u + 3]), 0.5f, bs.w) * 0.1f;
+                                continue;
+                            }
+#endif
                             tg[4 * u + 0] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 0]), 0.5f, bs.x));
                             tg[4 * u + 1] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 1]), 0.5f, bs.y));
                             tg[4 * u + 2] = tanh_approx(__uint_as_float(r[4 * u + 2]) + bs.z);
@@ -291,7 +320,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                             cn[u] = fmaf(gf, cp[u], gi * tg[4 * u + 2]);
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) hv[u] = fmaf(tg[4 * u + 3], 0.5f, 0.5f) * tanh_approx(cn[u]);
+                        for (int u = 0; u < 4; ++u) hv[u] = fmaf(tg[4 * u + 3], 0.5f, 0.5f) * ((APE_EXP == 7 && (s & 1)) ? cn[u] * 0.1f : tanh_approx(cn[u]));
 #else
                         float ev[16], num[4], den[4];
 #pragma unroll
@@ -385,8 +414,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
         }
     } else if (warp < MMA_WARP) {
         // =================================== operand-loader warps: x_t -> sAx ===========================================
-        const int row_l = (tid - EPI_THREADS) & (ROWS - 1);    // two threads per row, each half of the x k-groups
-        const int half = (tid - EPI_THREADS) >> 7;
+        constexpr int TPR = LOAD_WARPS * 32 / ROWS;            // loader threads per row, each an equal share of the x k-groups
+        const int row_l = (tid - EPI_THREADS) & (ROWS - 1);
+        const int part = (tid - EPI_THREADS) / ROWS;
         uint32_t gl = 0;                                       // steps loaded so far: step gl goes to x buffer gl & 1
         for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
             const int row = (tile * 2 + (int)rank) * a.rpc + row_l;
@@ -406,24 +436,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     if (a.in_mode == tc::IN_UNITS) src += ((((size_t)tile * T + t) * 2 + rank) * KG) * ROWS + row_l;
                     else src += ((((size_t)(e >> (a.in_rpc_shift + 1)) * T + t) * 2 + ((e >> a.in_rpc_shift) & 1)) * KG) * ROWS +
                                 (e & ((1 << a.in_rpc_shift) - 1));
-                    constexpr int KH = KG / 2, BK = 8;
-                    static_assert(KH == 2 * BK, "two batches of 8 k-groups per loader thread");
-                    const int j0 = half * KH;
+                    constexpr int KH = KG / TPR, BK = 8;        // k-groups per loader thread, in batches of 8 (register budget)
+                    static_assert(KH % BK == 0, "whole batches");
+                    const int j0 = part * KH;
                     src += (size_t)j0 * ROWS;
                     const uint32_t stream = a.stream_id0 + (uint32_t)b;
-                    // Everything that does not need the x tile happens BEFORE "the previous x tile has been consumed": batch 0 is
-                    // fetched and masked, and the Philox keep-bits of batch 1 are drawn (8 bits per k-group: the 16 units of the
-                    // second batch would not fit the register file).  Behind the wait: two rounds of stores and one of loads.
-                    uint4 pre[BK];
-                    uint32_t bits1[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-                    auto fetch = [&](int b0) {
+                    // x_t is double-buffered, so the loader runs a step ahead of the MMAs and none of this (Philox draws included)
+                    // sits on the step boundary; only the first store of a step waits for "the tile of two steps ago is consumed".
+#pragma unroll 1
+                    for (int b0 = 0; b0 < KH; b0 += BK) {
+                        uint4 pre[BK];
 #pragma unroll
                         for (int jj = 0; jj < BK; ++jj) pre[jj] = valid ? __ldg(src + (size_t)(b0 + jj) * ROWS) : make_uint4(0, 0, 0, 0);
-                    };
-                    auto mask_injected = [&](int b0) {
+                        if (a.mask_mode == APE_MASK_PHILOX) {
 #pragma unroll
-                        for (int jj = 0; jj < BK; ++jj) {
-                            if (valid) {
+                            for (int jj = 0; jj < BK; ++jj) {
+                                const uint4 m = philox_keep_halfmask(a.seed, stream, (uint32_t)f, (uint32_t)smp, (uint32_t)a.gap, (uint32_t)t,
+                                                                     (uint32_t)(j0 + b0 + jj), a.keep_thr16);
+                                pre[jj].x &= m.x; pre[jj].y &= m.y; pre[jj].z &= m.z; pre[jj].w &= m.w;
+                            }
+                        } else if (a.mask_mode == APE_MASK_INJECTED && valid) {
+#pragma unroll
+                            for (int jj = 0; jj < BK; ++jj) {
                                 const uint2 m = __ldg(reinterpret_cast<const uint2*>(
                                     a.masks + ((((size_t)e * a.n_gaps + a.gap) * T + t) * a.n + smp) * H + (j0 + b0 + jj) * 8));
                                 pre[jj].x &= ((m.x & 0xFFu) ? 0xFFFFu : 0u) | ((m.x & 0xFF00u) ? 0xFFFF0000u : 0u);
@@ -432,46 +466,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                                 pre[jj].w &= ((m.y & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.y & 0xFF000000u) ? 0xFFFF0000u : 0u);
                             }
                         }
-                    };
-                    auto store = [&](int b0) {
+                        if (b0 == 0) {
+                            if (trl) a.trace[580] = clock64();
+                            wait_buffer();
+                            if (trl) a.trace[581] = clock64();
+                        }
 #pragma unroll
                         for (int jj = 0; jj < BK; ++jj) *reinterpret_cast<uint4*>(sX + unit_offset(ROWS, row_l, j0 + b0 + jj)) = pre[jj];
-                    };
-                    fetch(0);
-                    if (a.mask_mode == APE_MASK_PHILOX) {
-#pragma unroll
-                        for (int jj = 0; jj < BK; ++jj) {
-                            const uint4 m = philox_keep_halfmask(a.seed, stream, (uint32_t)f, (uint32_t)smp, (uint32_t)a.gap, (uint32_t)t,
-                                                                 (uint32_t)(j0 + jj), a.keep_thr16);
-                            pre[jj].x &= m.x; pre[jj].y &= m.y; pre[jj].z &= m.z; pre[jj].w &= m.w;
-                        }
-#pragma unroll
-                        for (int jj = 0; jj < BK; ++jj) {
-                            const uint32_t k8 = philox_keep8(a.seed, stream, (uint32_t)f, (uint32_t)smp, (uint32_t)a.gap, (uint32_t)t,
-                                                             (uint32_t)(j0 + BK + jj), a.keep_thr16);
-                            bits1[jj >> 2] = (bits1[jj >> 2] & ~(0xFFu << (8 * (jj & 3)))) | (k8 << (8 * (jj & 3)));
-                        }
-                    } else if (a.mask_mode == APE_MASK_INJECTED) {
-                        mask_injected(0);
                     }
-                    if (trl) a.trace[580] = clock64();
-                    wait_buffer();
-                    if (trl) a.trace[581] = clock64();
-                    store(0);
-                    fetch(BK);
-                    if (a.mask_mode == APE_MASK_PHILOX) {
-#pragma unroll
-                        for (int jj = 0; jj < BK; ++jj) {      // keep-bit 2i -> low half of word i, 2i+1 -> high half
-                            const uint32_t k8 = bits1[jj >> 2] >> (8 * (jj & 3));
-                            pre[jj].x &= ((0u - (k8 & 1u)) & 0xFFFFu) | ((0u - ((k8 >> 1) & 1u)) & 0xFFFF0000u);
-                            pre[jj].y &= ((0u - ((k8 >> 2) & 1u)) & 0xFFFFu) | ((0u - ((k8 >> 3) & 1u)) & 0xFFFF0000u);
-                            pre[jj].z &= ((0u - ((k8 >> 4) & 1u)) & 0xFFFFu) | ((0u - ((k8 >> 5) & 1u)) & 0xFFFF0000u);
-                            pre[jj].w &= ((0u - ((k8 >> 6) & 1u)) & 0xFFFFu) | ((0u - ((k8 >> 7) & 1u)) & 0xFFFF0000u);
-                        }
-                    } else if (a.mask_mode == APE_MASK_INJECTED) {
-                        mask_injected(BK);
-                    }
-                    store(BK);
                 } else {                                       // layer 0: fp32 features (window of the ring, or dense rows)
                     wait_buffer();
                     const float* src = nullptr;
@@ -484,7 +486,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                             src = reinterpret_cast<const float*>(a.in) + ((size_t)b * a.feat_ring + fw % a.feat_ring) * a.Kin;
                         }
                     }
-                    for (int j = half; j < kgx; j += 2) {
+                    for (int j = part; j < kgx; j += TPR) {
                         float v[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) v[k] = (valid && 8 * j + k < a.Kin) ? __ldg(src + 8 * j + k) : 0.0f;
@@ -498,48 +500,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 if (trl) a.trace[582] = clock64();
             }
         }
-    } else if (warp == MMA_WARP) {
+    } else if (warp < TMA_WARP) {
         if (rank == 0) {
-            // =============================== MMA issuer (leader CTA; the whole warp runs, one elected lane issues) ======
+            // =============================== MMA issuers (leader CTA; the whole warp runs, one elected lane issues) =====
+            // Issuer k owns the chunks of accumulator slot k: a single issuing thread spends ~650 cycles of waits and table
+            // handling per piece plus ~34 cycles per MMA and was the bottleneck of the step (82 % busy).  Both issuers walk
+            // the whole table (the ring position and the piece sequence number advance with every entry) and act on their own
+            // entries only; tcgen05.commit covers the issuing thread's own MMAs, which is exactly what each hand-off needs.
+            const uint32_t my_slot = (uint32_t)(warp - MMA_WARP);
             const uint32_t idesc = make_idesc_f16(256, 128);
             const uint64_t dX0 = make_desc(smem_u32(sAx), LBO_A, SBO), dW = make_desc(smem_u32(sW), LBO_B, SBO);
             const uint32_t bar_full = smem_u32(&bars[C::BAR_W_FULL]), bar_empty = smem_u32(&bars[C::BAR_W_EMPTY]);
-            uint32_t gl = 0, wslot = 0, wphase = 0, gchunk = 0, hphase = 0;
+            uint32_t gl = 0, wslot = 0, gpiece = 0, gchunk = 0, hphase = 0;
             for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
                 for (int t = 0; t < T; ++t, ++gl) {
-                    long long* tr = (a.trace && blockIdx.x == 0 && tile == cluster_id && t == TRACE_T && lane == 0) ? a.trace : nullptr;
+                    TCS_TR(long long* tr = (a.trace && blockIdx.x == 0 && tile == cluster_id && t == TRACE_T && lane == 0) ? a.trace : nullptr;)
                     const uint32_t xb = gl & 1;                // x_t's buffer
                     mbar_wait_wd(&bars[C::BAR_X_READY + xb], (gl >> 1) & 1);
-                    if (tr) tr[576] = clock64();
+                    TCS_TR(if (tr) tr[576] = clock64();)
                     const uint64_t dX = dX0 + xb * (C::A_BYTES >> 4);
                     const uint32_t h_prev = tmem + H_COL + (uint32_t)(t & 1) * H_COLS;   // TMEM columns of h_{t-1}
                     const int which = t == 0 ? 0 : 1;
                     const uint32_t n_ent = sched.n[which];
                     uint32_t h_waited = 0;                     // K-slices of h_{t-1} seen so far in this step
+                    uint2 e = sched.e[which][0];
 #pragma unroll 1
                     for (uint32_t i = 0; i < n_ent; ++i) {
-                        const uint2 e = sched.e[which][i];
-                        if (e.x & E_PRE_SLOT) {                // the epilogue has drained the chunk that used this slot before
-                            if (gchunk >= NSLOT) mbar_wait_wd(&bars[C::BAR_SLOT_FREE + (e.x & E_SLOT1)], ((gchunk >> 1) & 1) ^ 1);
-                            ++gchunk;
-                            if (tr) tr[560 + ((gchunk - 1) & 7)] = clock64();
-                        }
-                        // the piece is in BOTH CTAs' rings: one slot, or two consecutive ones (> 8 MMAs)
+                        const uint2 e_next = sched.e[which][i + 1 < n_ent ? i + 1 : i];   // fetched under this piece's waits
                         const uint32_t nmma = (e.x >> E_NMMA_SHIFT) & 0x1F;
-                        const uint32_t slot_b = wslot + 1 == NP ? 0 : wslot + 1, phase_b = wslot + 1 == NP ? wphase ^ 1 : wphase;
+                        const uint32_t slot_b = wslot + 1 == NP ? 0 : wslot + 1;
+                        if ((e.x & E_SLOT1) != my_slot) {      // the other issuer's piece: only the ring bookkeeping advances
+                            wslot = nmma > SLOT_KG / 2 ? slot_b : wslot;
+                            wslot = wslot + 1 == NP ? 0 : wslot + 1;
+                            ++gpiece;
+                            e = e_next;
+                            continue;
+                        }
+                        if (e.x & E_PRE_SLOT) {                // the epilogue has drained the chunk that used this slot before
+                            if (gchunk >= 1) mbar_wait_wd(&bars[C::BAR_SLOT_FREE + my_slot], (gchunk & 1) ^ 1);
+                            ++gchunk;                          // (this issuer's count = uses of its slot so far)
+                            TCS_TR(if (tr) tr[560 + ((2 * (gchunk - 1) + my_slot) & 7)] = clock64();)
+                        }
+                        // the piece is in BOTH CTAs' rings (one slot, or two consecutive ones for > 8 MMAs): one barrier per piece
                         uint32_t spins = 0;
-                        while (!mbar_try_wait_addr(bar_full + wslot * 8, wphase)) { if (++spins > (1u << 24)) __trap(); }
-                        if (nmma > SLOT_KG / 2) while (!mbar_try_wait_addr(bar_full + slot_b * 8, phase_b)) { if (++spins > (1u << 24)) __trap(); }
+                        while (!mbar_try_wait_addr(bar_full + (gpiece & (C::NFULL - 1)) * 8, (gpiece / C::NFULL) & 1)) { if (++spins > (1u << 24)) __trap(); }
                         // LAST, because it is what the step boundary waits for: the K-slices of h_{t-1} this piece multiplies have
                         // been published.  Every epilogue warp publishes its slices in order, so slice k complete implies k-1, ...
                         const uint32_t hneed = (e.x >> E_HNEED_SHIFT) & 0xF;
                         if (hneed > h_waited) {
                             mbar_wait_wd(&bars[C::BAR_H_READY + hneed - 1], hphase);
-                            if (tr) tr[568 + hneed - 1] = clock64();
+                            TCS_TR(if (tr) tr[568 + hneed - 1] = clock64();)
                             h_waited = hneed;
                         }
                         fence_after_sync();
-                        if (tr && i < 48) { tr[2 * i] = clock64(); tr[600 + i] = spins; }
+                        TCS_TR(if (tr && i < 48) { tr[2 * i] = clock64(); tr[600 + i] = spins; })
                         if (elect_one()) {
                             const uint64_t bd = dW + wslot * (SLOT_BYTES >> 4), bd_b = dW + slot_b * (SLOT_BYTES >> 4);
                             const uint32_t d_tmem = tmem + (e.x & E_SLOT1) * 128;
@@ -575,55 +589,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                             if (e.x & E_POST_X) commit_pair(&bars[C::BAR_X_DONE + xb], 0x3);
                         }
                         __syncwarp();
-                        if (tr && i < 48) tr[2 * i + 1] = clock64();
-                        if (nmma > SLOT_KG / 2) { wslot = slot_b; wphase = phase_b; }
-                        if (++wslot == NP) { wslot = 0; wphase ^= 1; }
+                        TCS_TR(if (tr && i < 48) tr[2 * i + 1] = clock64();)
+                        wslot = nmma > SLOT_KG / 2 ? slot_b : wslot;
+                        wslot = wslot + 1 == NP ? 0 : wslot + 1;
+                        ++gpiece;
+                        e = e_next;
                     }
                     if (t > 0) hphase ^= 1;
                 }
             }
-        } else if (lane == 0) {
+        } else if (warp == MMA_WARP && lane == 0) {
             // =============================== peer CTA: forward "piece landed in my ring" to the leader ==================
-            uint32_t wslot = 0, wphase = 0;
+            uint32_t gpiece = 0;
             for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters)
                 for (int t = 0; t < T; ++t) {
-                    const int which = t == 0 ? 0 : 1;
-                    const uint32_t n_ent = sched.n[which];
+                    const uint32_t n_ent = sched.n[t == 0 ? 0 : 1];
 #pragma unroll 1
-                    for (uint32_t i = 0; i < n_ent; ++i) {
-                        const uint32_t n_slots = ((sched.e[which][i].x >> E_NMMA_SHIFT) & 0x1F) > SLOT_KG / 2 ? 2 : 1;
-                        for (uint32_t k = 0; k < n_slots; ++k) {
-                            mbar_wait_wd(&bars[C::BAR_W_FULL + wslot], wphase);
-                            mbar_arrive_remote(&bars[C::BAR_W_FULL + wslot], 0);
-                            if (++wslot == NP) { wslot = 0; wphase ^= 1; }
-                        }
+                    for (uint32_t i = 0; i < n_ent; ++i, ++gpiece) {
+                        mbar_wait_wd(&bars[C::BAR_W_FULL + (gpiece & (C::NFULL - 1))], (gpiece / C::NFULL) & 1);
+                        mbar_arrive_remote(&bars[C::BAR_W_FULL + (gpiece & (C::NFULL - 1))], 0);
                     }
                 }
         }
     } else if (lane == 0) {
         // =================================== weight-ring producer (one lane per CTA) =====================================
         const uint8_t* Wc = a.W + (size_t)rank * w_bytes;      // this CTA's half of the layer's weight tiles
-        uint32_t wslot = 0, wphase = 0;
+        uint32_t wslot = 0, wphase = 0, gpiece = 0;
         bool wrapped = false;
         for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters)
             for (int t = 0; t < T; ++t) {
-                long long* tr = (a.trace && blockIdx.x == 0 && tile == cluster_id && t == TRACE_T) ? a.trace : nullptr;
+                TCS_TR(long long* tr = (a.trace && blockIdx.x == 0 && tile == cluster_id && t == TRACE_T) ? a.trace : nullptr;)
                 const int which = t == 0 ? 0 : 1;
                 const uint32_t n_ent = sched.n[which];
 #pragma unroll 1
-                for (uint32_t i = 0; i < n_ent; ++i) {
+                for (uint32_t i = 0; i < n_ent; ++i, ++gpiece) {
                     const uint32_t ex = sched.e[which][i].x;
                     uint32_t kg_left = ((ex >> E_NMMA_SHIFT) & 0x1F) * 2, src_kg = ex >> E_SRC_SHIFT;
-                    if (tr && i < 48) tr[256 + 2 * i] = clock64();
+                    uint64_t* full = &bars[C::BAR_W_FULL + (gpiece & (C::NFULL - 1))];      // one "landed" barrier per piece
+                    TCS_TR(if (tr && i < 48) tr[256 + 2 * i] = clock64();)
+                    bool first = true;
                     while (kg_left > 0) {                      // one or two slots
                         const uint32_t kg = kg_left < (uint32_t)SLOT_KG ? kg_left : (uint32_t)SLOT_KG, bytes = kg * KG_BYTES_B;
                         if (wrapped) mbar_wait_wd(&bars[C::BAR_W_EMPTY + wslot], wphase ^ 1);   // previous occupant consumed
-                        mbar_arrive_expect_tx(&bars[C::BAR_W_FULL + wslot], bytes);
-                        bulk_g2s(sW + wslot * SLOT_BYTES, Wc + (size_t)src_kg * KG_BYTES_B, bytes, &bars[C::BAR_W_FULL + wslot]);
+                        if (first) mbar_arrive_expect_tx(full, kg_left * KG_BYTES_B);           // all bytes of the piece
+                        first = false;
+                        bulk_g2s(sW + wslot * SLOT_BYTES, Wc + (size_t)src_kg * KG_BYTES_B, bytes, full);
                         kg_left -= kg; src_kg += kg;
                         if (++wslot == NP) { wslot = 0; wphase ^= 1; wrapped = true; }
                     }
-                    if (tr && i < 48) tr[257 + 2 * i] = clock64();
+                    TCS_TR(if (tr && i < 48) tr[257 + 2 * i] = clock64();)
                 }
             }
     }
