@@ -302,7 +302,7 @@ def run_ours(args, rank, world, local_rank):
                     "frac_of_bf16_tensor_peak": achieved / peaks["bf16_tflops"]}
     # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r1_final_ncu_summary.md:
     # dram__bytes_read.sum + dram__bytes_write.sum of launch 1); null for configurations that were not captured
-    traffic = {("tc", 128, 1024, 100): 2.005248e6 + 102.449152e6, ("tc", 256, 1024, 100): 5.376768e6 + 0.032e6}.get(
+    traffic = {("tc", 128, 1024, 100): 2.005248e6 + 102.449152e6, ("tc", 256, 1024, 100): 5.361920e6 + 512.0}.get(
         (be.lstm_variant, H, count, n)) if args.workload in ("uarm_1024x100", "watch_only_1024x100") else None
     roofline.update({"flops_per_launch": dom_flops, "ms_per_launch": dom_ms, "layer_ms": [float(v) for v in acc], "traffic": traffic,
                      "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_final_ncu_summary.md)"})
