@@ -37,9 +37,18 @@ constexpr int ROWS = 128;                          // rows per CTA = TMEM lanes
 
 enum { BAR_X_READY = 0, BAR_X_DONE = 1, BAR_ACC_READY = 2, BAR_SLOT_FREE = 6, BAR_H_READY = 10, BAR_COUNT = 14 };
 
-// role 0 = epilogue warp 0 (chunk 0), role 1 = loader warp 16, role 2 = MMA issuer; only block 0, first tile, lane 0
+// Tracing (tools/tc_trace.py) is a compile-time option: even predicated off, the stamps cost every epilogue warp ~40 issue slots per
+// chunk.  Build with -DAPE_TC_TRACE=1 to get them: role 0 = epilogue warp 0 (chunk 0), role 1 = loader warp 16, role 2 = MMA issuer;
+// only block 0, first tile, lane 0.
+#ifndef APE_TC_TRACE
+#define APE_TC_TRACE 0
+#endif
+#if APE_TC_TRACE
 #define APE_TRACE(role, t, ev) do { if (a.trace && blockIdx.x == 0 && tile == cluster_id && lane == 0 && (t) < 16) \
     a.trace[((role) * 16 + (t)) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define APE_TRACE(role, t, ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 

@@ -57,14 +57,14 @@ constexpr uint32_t SLOT_BYTES = SLOT_KG * KG_BYTES_B;    // ring slot = 16 KB
 constexpr uint32_t BAR_BLOCK_BYTES = 512;
 constexpr uint32_t SMEM_LIMIT = 227 * 1024;
 #ifndef APE_TCS_TRACE
-#define APE_TCS_TRACE 0      // 1: the issuer / producer loops stamp SM clocks into args.trace (tools/tcs_trace.py); costs issue time
+#define APE_TCS_TRACE 0      // 1: all roles stamp SM clocks into args.trace (tools/tcs_trace.py); compiled out by default: costs issue slots
 #endif
 #if APE_TCS_TRACE
 #define TCS_TR(...) __VA_ARGS__
+constexpr int TRACE_T = 3;                         // the step of the first tile of CTA 0 that is stamped
 #else
 #define TCS_TR(...)
 #endif
-constexpr int TRACE_T = 3;                         // tracing (args.trace): the step of the first tile of CTA 0 that is stamped
 
 template <int H> struct Cfg {
     static constexpr int NCH = H / 32, KG = H / 8;
@@ -274,8 +274,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                             tmem_ld_x16(tmem + t_lane + (uint32_t)((c & 1) * 128 + 32 * s), rbuf[hp & 1]);
                         }
                         tmem_ld_wait();                        // this half-pass's columns have landed
-                        if (a.trace && blockIdx.x == 0 && tile == cluster_id && warp == 0 && lane == 0 && (t == TRACE_T || t == TRACE_T - 1))
-                            a.trace[512 + (t - TRACE_T + 1) * 16 + hp] = clock64();
+                        TCS_TR(if (a.trace && blockIdx.x == 0 && tile == cluster_id && warp == 0 && lane == 0 && (t == TRACE_T || t == TRACE_T - 1))
+                                   a.trace[512 + (t - TRACE_T + 1) * 16 + hp] = clock64();)
                         if (half == 1) {                       // chunk c fully drained: the issuer may refill its slot
                             fence_before_sync();
                             __syncwarp();
@@ -433,7 +433,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 uint8_t* sX = sAx + (gl & 1) * C::A_BYTES;
                 // the tile written two steps ago has been consumed (the loader may run up to two steps ahead of the MMAs)
                 auto wait_buffer = [&]() { if (gl >= 2) mbar_wait_wd(&bars[C::BAR_X_DONE + (gl & 1)], ((gl >> 1) & 1) ^ 1); };
-                const bool trl = a.trace && blockIdx.x == 0 && tile == cluster_id && t == TRACE_T && tid == EPI_THREADS;
+                TCS_TR(const bool trl = a.trace && blockIdx.x == 0 && tile == cluster_id && t == TRACE_T && tid == EPI_THREADS;)
                 if (a.in_mode == tc::IN_UNITS || a.in_mode == tc::IN_SHARED_UNITS) {
                     // The first batch of 8 k-groups is fetched and masked before anything waits; only the shared-memory
                     // stores (and the remaining batches, which would not fit the register file) sit behind "the previous
@@ -473,9 +473,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                             }
                         }
                         if (b0 == 0) {
-                            if (trl) a.trace[580] = clock64();
+                            TCS_TR(if (trl) a.trace[580] = clock64();)
                             wait_buffer();
-                            if (trl) a.trace[581] = clock64();
+                            TCS_TR(if (trl) a.trace[581] = clock64();)
                         }
 #pragma unroll
                         for (int jj = 0; jj < BK; ++jj) *reinterpret_cast<uint4*>(sX + unit_offset(ROWS, row_l, j0 + b0 + jj)) = pre[jj];
@@ -503,7 +503,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&bars[C::BAR_X_READY + (gl & 1)], rank);
-                if (trl) a.trace[582] = clock64();
+                TCS_TR(if (trl) a.trace[582] = clock64();)
             }
         }
     } else if (warp < TMA_WARP) {

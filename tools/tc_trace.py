@@ -1,4 +1,5 @@
-"""Timeline of one CTA of the tensor-core LSTM kernel (SM-clock stamps written by the kernel when a trace buffer is given)."""
+"""Timeline of one CTA of the tensor-core LSTM kernel (SM-clock stamps written by the kernel when a trace buffer is given).
+Needs a library built with -DAPE_TC_TRACE=1 (the stamps are compiled out by default): APE_B200_LIB=<that .so> python tools/tc_trace.py"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))

@@ -1,5 +1,6 @@
 """Timeline of one step of CTA 0 of the streamed-weights tensor-core LSTM kernel (H = 256): per weight piece the issuer's
-wait / issue stamps and the producer's slot-free / copy-issued stamps, plus the epilogue's half-pass starts."""
+wait / issue stamps and the producer's slot-free / copy-issued stamps, plus the epilogue's half-pass starts.
+The stamps need a library built with -DAPE_TCS_TRACE=1 (APE_B200_LIB=<that .so>)."""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
