@@ -25,7 +25,8 @@ SYMBOLS = (
     "ape_abi_version", "ape_last_cuda_error", "ape_device_info", "ape_lstm_blob_floats", "ape_features",
     "ape_mc_lstm_workspace_bytes", "ape_mc_lstm_fma", "ape_mc_lstm_tc_supported", "ape_lstm_tc_blob_bytes",
     "ape_mc_lstm_tc_workspace_bytes", "ape_mc_lstm_tc", "ape_philox_masks", "ape_ff_blob_floats", "ape_mc_ff", "ape_fk_reduce", "ape_msg_from_est",
-    "ape_selfcheck_philox", "ape_selfcheck_keep8", "ape_selfcheck_features", "ape_selfcheck_row_pose", "ape_selftest_umma",
+    "ape_selfcheck_philox", "ape_selfcheck_keep8", "ape_selfcheck_features", "ape_selfcheck_row_pose", "ape_selfcheck_tcs_schedule",
+    "ape_selftest_umma",
 )
 
 
@@ -116,6 +117,8 @@ def load():
     lib.ape_selfcheck_features.argtypes = [i32, i32, C.POINTER(f32), C.POINTER(C.c_double), C.POINTER(i32)]
     lib.ape_selfcheck_row_pose.restype = i32
     lib.ape_selfcheck_row_pose.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double), i32, C.POINTER(C.c_double), C.POINTER(i32)]
+    lib.ape_selfcheck_tcs_schedule.restype = i32
+    lib.ape_selfcheck_tcs_schedule.argtypes = [i32, i32, C.POINTER(u32), i32, C.POINTER(i32)]
     lib.ape_selftest_umma.restype = i32
     lib.ape_selftest_umma.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     _lib = lib

@@ -678,3 +678,18 @@ int launch_layer(int H, const TcLayerArgs& a, int sm_count, cudaStream_t st) {
 
 }  // namespace tcs
 }  // namespace ape
+
+// Host self-check hook (tests only): the step schedule of the streamed-weights kernel for an x-part of kgx k-groups.
+// entries: [n][2] words (.x flags / MMAs / K-slices needed / weight offset, .y A-operand offset), see the E_* bits above.
+extern "C" int ape_selfcheck_tcs_schedule(int kgx, int first_step, uint32_t* entries, int max_entries, int* n_entries) {
+    using namespace ape::tcs;
+    using C = Cfg<256>;
+    if (!entries || !n_entries || kgx < 2 || kgx > C::KG || (kgx & 1)) return APE_ERR_BAD_ARG;
+    Schedule sched{};
+    Recorder r{sched.e[0], 0, kgx, C::KG, 0u, false};
+    walk_step<C::NCH>(first_step != 0, kgx, r);
+    if (r.overflow || r.n > max_entries) return APE_ERR_UNSUPPORTED;
+    for (int i = 0; i < r.n; ++i) { entries[2 * i] = sched.e[0][i].x; entries[2 * i + 1] = sched.e[0][i].y; }
+    *n_entries = r.n;
+    return APE_OK;
+}

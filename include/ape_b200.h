@@ -193,6 +193,10 @@ int ape_selfcheck_keep8(uint64_t seed, uint32_t stream, uint32_t frame, uint32_t
                         uint32_t t, uint32_t group, float dropout_p, uint32_t* keep_bits);
 int ape_selfcheck_features(int kind, int layout, const float* row, double* xx, int* n_features);
 int ape_selfcheck_row_pose(int target, const double* preds, const double* body9, int use_float, double* est, int* bad);
+/* The per-step schedule of weight pieces of the H = 256 tensor-core kernel (csrc/ape_lstm_tcs.cu: walk_step) for an x-part of kgx
+ * k-groups: entries [n][2] words; lets a CPU-only box check that every chunk's operands are covered exactly once, in an order
+ * the ring can serve. */
+int ape_selfcheck_tcs_schedule(int kgx, int first_step, uint32_t* entries, int max_entries, int* n_entries);
 /* GPU self-test of the tcgen05 / TMEM plumbing: D[128*cta_group][N] (f32) = A * B^T with f16 operands packed in the
  * canonical K-major no-swizzle layout of csrc/ape_umma.cuh (a_packed: [cta][K/8][128][8], b_packed: [cta][K/8][N/cta][8]).
  * cta_group 1 | 2; + 16 routes the A operand through tensor memory (tcgen05.st, then the [a_tmem] form of tcgen05.mma). */

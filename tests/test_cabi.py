@@ -82,3 +82,51 @@ def test_sass_is_sm100a():
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in out.stdout
+
+
+@pytest.mark.parametrize("kgx", [2, 4, 6, 32])
+def test_tcs_schedule_covers_every_operand_once(kgx):
+    """The H = 256 tensor-core kernel streams its weights in the order of a host-built table (csrc/ape_lstm_tcs.cu: walk_step).
+    Every chunk must see its x k-groups [0, kgx) and - after the first step - its recurrent k-groups [0, 32) exactly once, the
+    first MMA of a chunk must overwrite the accumulator, recurrent pieces may only need K-slices that are published by then,
+    each accumulator slot's last x-part must release the x tile, and a piece must fit two ring slots."""
+    import ctypes as C
+    lib = N.load()
+    NCH, SLICE_KG, SLOT_KG = 8, 4, 16
+    for first_step in (1, 0):
+        buf = (C.c_uint32 * (2 * 64))()
+        n = C.c_int(0)
+        assert lib.ape_selfcheck_tcs_schedule(kgx, first_step, buf, 64, C.byref(n)) == N.APE_OK
+        ent = [(buf[2 * i], buf[2 * i + 1]) for i in range(n.value)]
+        cover_x = {c: [] for c in range(NCH)}
+        cover_h = {c: [] for c in range(NCH)}
+        begun, done, x_done = [], [], []
+        for x, y in ent:
+            slot, is_h, first = x & 1, bool(x & 2), bool(x & 4)
+            nmma, hneed, src = (x >> 8) & 0x1F, (x >> 13) & 0xF, x >> 17
+            assert 1 <= nmma <= 2 * (SLOT_KG // 2)
+            chunk_rel, off = divmod(src, kgx + 32)                     # k-group offset inside this CTA's weight tiles
+            assert chunk_rel % 2 == slot
+            if x & 8:
+                begun.append(chunk_rel)
+            if is_h:
+                kg0 = off - kgx
+                assert kg0 >= 0 and y == kg0 * 4 and not first
+                assert hneed == -(-(kg0 + 2 * nmma) // SLICE_KG)       # needs exactly the K-slices it multiplies
+                cover_h[chunk_rel] += list(range(kg0, kg0 + 2 * nmma))
+            else:
+                assert off + 2 * nmma <= kgx and y == off * 128 and hneed == 0
+                assert first == (off == 0)
+                cover_x[chunk_rel] += list(range(off, off + 2 * nmma))
+            if x & 16:
+                done.append(chunk_rel)
+            if x & 32:
+                x_done.append(chunk_rel)
+        for c in range(NCH):
+            assert sorted(cover_x[c]) == list(range(kgx))
+            assert sorted(cover_h[c]) == ([] if first_step else list(range(32)))
+        assert begun == list(range(NCH)) and sorted(done) == list(range(NCH)) and x_done == [NCH - 2, NCH - 1]
+        if not first_step:                                              # only ONE small piece may follow the last K-slice of h_t
+            last_slice = [i for i, (x, _) in enumerate(ent) if (x >> 13) & 0xF == NCH]
+            assert ((ent[last_slice[0]][0] >> 8) & 0x1F) == SLICE_KG // 2 and ent[last_slice[0]][0] & 16
+    assert lib.ape_selfcheck_tcs_schedule(3, 0, buf, 64, C.byref(n)) == N.APE_ERR_BAD_ARG
