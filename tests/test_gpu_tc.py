@@ -1,6 +1,7 @@
-"""GPU (-m gpu): the tcgen05 tensor-core LSTM path (fp16 operands, fp32 accumulate) against the oracle, the golden
-reference messages and the fp32 kernel.  Tolerance: 1e-4 m on positions (north_star's bound); measured errors are
-printed - with the seeded weights they are ~5e-6 m."""
+"""GPU (-m gpu): the two tcgen05 tensor-core LSTM kernels (fp16 operands, fp32 accumulate; H <= 128 with resident weights,
+H = 256 with TMA-streamed weights and h_t in tensor memory) against the oracle, the golden reference messages and the fp32
+kernel.  Tolerance: 1e-4 m on positions (north_star's bound); measured errors are printed - with the seeded weights they are
+~5e-6 .. 2.6e-5 m."""
 import numpy as np
 import pytest
 import torch
