@@ -215,3 +215,25 @@ def test_tc_odd_shapes_against_oracle(I, H, L, T, O, E, n):
           f"tc vs fp32 over all rows {np.abs(got_tc - got_32).max():.3g}")
     assert worst_32 <= 2e-5
     assert worst_tc <= 2e-4 and np.abs(got_tc - got_32).max() <= 2e-4        # fp16 operands (measured <= 9e-6 on |pred| ~ 0.08)
+
+
+def test_tc_random_shapes_match_the_fp32_kernel():
+    # 24 seeded random (I, H, L, T, O, E, n) combinations, injected masks: the tensor-core kernels (both of them, all input modes,
+    # ragged tiles, more tiles than CTA pairs for small E * n is not reachable here - see the 1024 x 100 tests) against the fp32 kernel
+    rng = np.random.default_rng(2026)
+    worst = 0.0
+    for case in range(24):
+        H = int(rng.choice([64, 128, 256]))
+        I = int(rng.integers(1, min(H, 60) + 1))
+        L, T, O = int(rng.integers(2, 5)), int(rng.integers(1, 9)), int(rng.integers(1, 21))
+        E, n = int(rng.integers(1, 40)), int(rng.integers(1, 140))
+        p = float(rng.choice([0.0, 0.2, 0.5]))
+        state = syn.synth_state_dict(I, H, L, O, 1000 + case)
+        x = rng.normal(size=(E, T, I)).astype(np.float32)
+        masks = (rng.random(size=(E, L - 1, T, n, H)) < 1 - p).astype(np.uint8)
+        got_tc = _lstm_last_step(state, (I, H, L, T, O), x, n, masks, "tc", p)
+        got_32 = _lstm_last_step(state, (I, H, L, T, O), x, n, masks, "fp32", p)
+        err = float(np.abs(got_tc - got_32).max())
+        assert np.isfinite(got_tc).all() and err <= 3e-4, f"case {case}: I{I} H{H} L{L} T{T} O{O} E{E} n{n} p{p}: {err:.3g}"
+        worst = max(worst, err)
+    print(f"24 random shapes: worst |tensor-core - fp32| prediction difference {worst:.3g}")
