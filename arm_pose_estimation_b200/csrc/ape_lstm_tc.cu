@@ -35,7 +35,8 @@ constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS;
 constexpr int THREADS = (MMA_WARP + 1) * 32;       // 16 epilogue + 8 operand-loader + 1 MMA-issue warps = 800
 constexpr int ROWS = 128;                          // rows per CTA = TMEM lanes
 
-enum { BAR_X_READY = 0, BAR_X_DONE = 1, BAR_ACC_READY = 2, BAR_SLOT_FREE = 6, BAR_H_READY = 10, BAR_COUNT = 14 };
+enum { BAR_X_READY = 0, BAR_X_DONE = 1, BAR_ACC_READY = 2, BAR_SLOT_FREE = 6, BAR_H_READY = 10, BAR_OUT_READY = 14, BAR_OUT_DONE = 15, BAR_COUNT = 16 };
+constexpr uint32_t BAR_BLOCK_BYTES = 256;          // barriers + the TMEM base slot
 
 // Tracing (tools/tc_trace.py) is a compile-time option: even predicated off, the stamps cost every epilogue warp ~40 issue slots per
 // chunk.  Build with -DAPE_TC_TRACE=1 to get them: role 0 = epilogue warp 0 (chunk 0), role 1 = loader warp 16, role 2 = MMA issuer;
@@ -71,7 +72,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
     float* sBias = reinterpret_cast<float*>(sAx + A_BYTES);    // [4H]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 4 * H);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
-    uint8_t* sW = reinterpret_cast<uint8_t*>(bars) + 128;             // [w_bytes], after the 128-byte barrier block
+    uint8_t* sW = reinterpret_cast<uint8_t*>(bars) + BAR_BLOCK_BYTES; // [w_bytes], after the barrier block
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
@@ -96,6 +97,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
             mbar_init(&bars[BAR_SLOT_FREE + c], 2 * EPI_WARPS);
             mbar_init(&bars[BAR_H_READY + c], 2 * EPI_WARPS);   // the 32 hidden units of chunk c of h_t are in both CTAs' tiles
         }
+        mbar_init(&bars[BAR_OUT_READY], 1);
+        mbar_init(&bars[BAR_OUT_DONE], 2 * EPI_WARPS);
         mbar_init_fence();
     }
     fence_proxy_async_smem();
@@ -113,7 +116,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
         const int row_l = 32 * q + lane;                       // local row == TMEM lane
         const uint32_t t_lane = (uint32_t)(32 * q) << 16;
         const bool warp_live = 32 * q < a.rpc;                 // a quarter without rows only keeps the barrier protocol going
-        uint32_t ph_acc = 0;
+        uint32_t ph_acc = 0, ph_out = 0;
         float cst[NCH][8];
 
         for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
@@ -126,10 +129,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 
             for (int t = 0; t < T; ++t) {
                 uint8_t* sAh_next = sAh + ((t + 1) & 1) * A_BYTES;
-                uint8_t* sAh_prev = sAh + (t & 1) * A_BYTES;
-                // last step of the last layer: h_T feeds the output layer only - keep it in fp32, [unit][row], in the two
-                // h tiles (units < H/2 in the tile being written, the rest in the tile the last MMAs have finished reading)
-                const bool final_f32 = a.preds != nullptr && t == T - 1;
+                // last step of the last layer: h_T is published like every other h_t - the output layer is one more (small)
+                // tensor-core product  h_T x W_o^T  issued into the last accumulator chunk once that chunk has been drained
+                const bool final_out = a.preds != nullptr && t == T - 1;
                 if (warp == 0) APE_TRACE(0, t, 0);
                 if (!warp_live) {
 #pragma unroll
@@ -137,7 +139,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         mbar_wait(&bars[BAR_ACC_READY + c], ph_acc);
                         if (lane == 0) {
                             mbar_arrive_leader(&bars[BAR_SLOT_FREE + c], rank);
-                            if (t + 1 < T) mbar_arrive_leader(&bars[BAR_H_READY + c], rank);
+                            if (t + 1 < T || final_out) mbar_arrive_leader(&bars[BAR_H_READY + c], rank);
                         }
                     }
                 } else {
@@ -216,19 +218,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 #endif
 
                         const int j = 4 * c + s;               // k-group of units 32c + 8s .. + 7
-                        if (final_f32) {
-                            if (half == 0 && c >= NCH / 2 && c < NCH - 1) mbar_wait(&bars[BAR_ACC_READY + NCH - 1], ph_acc);   // every MMA retired
-                            // fp32 h_T as [row][H/2 units], 16-byte groups XOR-swizzled by the row so both this store and the
-                            // output layer's 128-bit reads are bank-conflict free
-                            const int grp = ((8 * j) % (H / 2)) / 4 + half;
-                            float4* dst = reinterpret_cast<float4*>(c < NCH / 2 ? sAh_next : sAh_prev) + row_l * (H / 8) + (grp ^ (row_l & (H / 8 - 1)));
-                            *dst = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                        } else if (half == 1) {
+                        if (half == 1) {
                             *reinterpret_cast<uint4*>(sAh_next + unit_offset(ROWS, row_l, j)) =
                                 make_uint4(pack_half2(hlo[0], hlo[1]), pack_half2(hlo[2], hlo[3]), pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]));
                         }
                         if (half == 1) {
-                            if (t + 1 < T) {                   // publish this chunk's slice of h_t: its K-slice of the next recurrent
+                            if (final_out && c == NCH - 1 && warp == 0) {
+                                // Output layer: this CTA's 16 of the 32 columns of the fp16 W_o tile (the leader holds the fp16 ROUNDING of
+                                // W_o for the 16 outputs, the peer the fp16 REMAINDER W_o - fp16(W_o): their products are summed, so only
+                                // h_T carries an fp16 rounding) go where h_{T-1} was - that tile is dead: this pass started after the LAST
+                                // accumulator of the step was complete, i.e. after every MMA that reads it had retired, and shared memory
+                                // has no room for a dedicated copy.  It is in place before this warp publishes the last slice of h_T.
+                                const uint4* wo = reinterpret_cast<const uint4*>(a.Wo16) + (size_t)rank * KG * 16;
+                                uint4* dst = reinterpret_cast<uint4*>(sAh + (t & 1) * A_BYTES);
+#pragma unroll
+                                for (int i = 0; i < KG * 16 / 32; ++i) dst[i * 32 + lane] = __ldg(wo + i * 32 + lane);
+                            }
+                            if (t + 1 < T || final_out) {      // publish this chunk's slice of h_t: its K-slice of the next recurrent
                                 fence_proxy_async_smem();      // product can be issued while later chunks still run
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive_leader(&bars[BAR_H_READY + c], rank);
@@ -247,45 +253,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     }
                 }
                 ph_acc ^= 1;
-                if (final_f32) {                               // output_layer (nn_models.py:189), last step only
+                if (final_out) {                               // output_layer (nn_models.py:189), last step only
                     if (warp == 0) APE_TRACE(0, t, 13);
-                    epi_bar_sync();
-                    if (valid) {
-                        const int e = row / a.n, smp = row - e * a.n;
-                        const int b = e / a.nF, fb = stream_frame0(a.stream_frames, a.frame0, b), f = fb + e % a.nF;
-                        // this thread: outputs o = s, s+4, ... of its row (<= 5 for O <= 20), all accumulated in one sweep over k
-                        // so every h value is read from shared memory once and the FMA chains are independent
-                        float acc[5];
+                    // the issuer multiplies the published h_T by W_o^T (fp16 operands, fp32 accumulate) into the first 16 columns
+                    // of the last accumulator chunk; every warp waits for it - also the guarantee that h_T has been consumed
+                    // before the next tile's cell updates rewrite the operand tiles
+                    mbar_wait(&bars[BAR_OUT_READY], ph_out);
+                    ph_out ^= 1;
+                    fence_after_sync();
+                    if (warp_live) {
+                        uint32_t o32[32];                      // columns 0..15: h_T x fp16(W_o)^T, 16..31: h_T x (W_o - fp16(W_o))^T
+                        tmem_ld_x32(tmem + t_lane + (uint32_t)((NCH - 1) * 128), o32);
+                        tmem_ld_wait();
+                        if (valid) {
+                            const int e = row / a.n, smp = row - e * a.n;
+                            const int b = e / a.nF, fb = stream_frame0(a.stream_frames, a.frame0, b), f = fb + e % a.nF;
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) acc[i] = (s + 4 * i < a.O) ? __ldg(a.bo + s + 4 * i) : 0.0f;
-#pragma unroll
-                        for (int part = 0; part < 2; ++part) {
-                            const float4* hp = reinterpret_cast<const float4*>(part == 0 ? sAh_next : sAh_prev) + row_l * (H / 8);
-                            const float* wp = a.Wo + part * (H / 2);
-#pragma unroll 4
-                            for (int gk = 0; gk < H / 8; ++gk) {
-                                const float4 x = hp[gk ^ (row_l & (H / 8 - 1))];
-#pragma unroll
-                                for (int i = 0; i < 5; ++i) {
-                                    if (s + 4 * i < a.O) {
-                                        const float4 w = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(s + 4 * i) * H + 4 * gk));
-                                        acc[i] = fmaf(w.x, x.x, acc[i]); acc[i] = fmaf(w.y, x.y, acc[i]);
-                                        acc[i] = fmaf(w.z, x.z, acc[i]); acc[i] = fmaf(w.w, x.w, acc[i]);
-                                    }
+                            for (int i = 0; i < 4; ++i) {      // this thread: outputs o = s, s+4, ... of its row (O <= 16)
+                                const int o = s + 4 * i;
+                                if (o < a.O && fb >= 0) {      // (an inactive stream keeps its prediction ring untouched)
+                                    const float y = __uint_as_float(o32[o]) + __uint_as_float(o32[16 + o]) + __ldg(a.bo + o);
+                                    float* dst = a.preds + (((size_t)b * a.pred_ring + f % a.pred_ring) * a.n_out) * a.O + o;
+                                    if (a.n == 1 && a.n_out > 1) for (int s2 = 0; s2 < a.n_out; ++s2) dst[(size_t)s2 * a.O] = y;
+                                    else dst[(size_t)smp * a.O] = y;
                                 }
                             }
                         }
-#pragma unroll
-                        for (int i = 0; i < 5; ++i) {
-                            const int o = s + 4 * i;
-                            if (o < a.O && fb >= 0) {  // (an inactive stream keeps its prediction ring untouched)
-                                float* dst = a.preds + (((size_t)b * a.pred_ring + f % a.pred_ring) * a.n_out) * a.O + o;
-                                if (a.n == 1 && a.n_out > 1) for (int s2 = 0; s2 < a.n_out; ++s2) dst[(size_t)s2 * a.O] = acc[i];
-                                else dst[(size_t)smp * a.O] = acc[i];
-                            }
-                        }
                     }
-                    epi_bar_sync();                            // the next tile's first cell update rewrites these tiles
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&bars[BAR_OUT_DONE], rank);   // the chunk may be refilled for the next tile
                     if (warp == 0) APE_TRACE(0, t, 14);
                 }
             }
@@ -375,9 +372,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
         //                                                              K-slices already published
         //   H_READY[c']   (units 32c'..32c'+31 of h_{t-1} published) -> recurrent pieces (c, c') of every chunk c <= c'
         // so when the last slice arrives only 2 MMAs stand between it and ACC_READY[0].
-        uint32_t ph_xready = 0, ph_hready = 0, ph_slot = 0;
+        uint32_t ph_xready = 0, ph_hready = 0, ph_slot = 0, ph_outdone = 0;
         bool first = true;
         constexpr int KS2 = 2;                                  // K=16 MMAs per 32-unit K-slice (4 k-groups)
+        // Output layer of the last layer (nn_models.py:189, last step only): h_T x [fp16(W_o) | W_o - fp16(W_o)]^T as KG/2 MMAs of
+        // N = 32 into the first columns of the LAST accumulator chunk, once that chunk has been drained and all of h_T has been
+        // published.  It is issued where the chunk would be refilled for the next tile (or after the last tile); the epilogue
+        // reads the 32 columns and hands the chunk back (OUT_DONE).
+        const uint32_t idesc_out = make_idesc_f16(256, 32);
+        const uint64_t dWo = make_desc(smem_u32(sAh + ((T - 1) & 1) * A_BYTES), 16 * 16, SBO);  // over the dead h_{T-1} tile
+        bool out_pending = false;
+        auto issue_output = [&]() {
+            for (int c = 0; c < NCH; ++c) mbar_wait(&bars[BAR_H_READY + c], ph_hready);
+            ph_hready ^= 1;
+            fence_after_sync();
+            if (elect_one()) {
+                const uint64_t dHT = desc_advance(dH0, (uint32_t)(T & 1) * A_BYTES);      // step T-1 wrote h_T into tile (T & 1)
+#pragma unroll
+                for (int k2 = 0; k2 < KG / 2; ++k2)
+                    mma_f16<2>(tmem + (NCH - 1) * 128, desc_advance(dHT, k2 * 2 * LBO_A), desc_advance(dWo, k2 * 2 * (16 * 16)), idesc_out, k2 > 0 ? 1u : 0u);
+                commit_pair(&bars[BAR_OUT_READY], 0x3);
+            }
+            __syncwarp();
+            mbar_wait(&bars[BAR_OUT_DONE], ph_outdone);         // every epilogue warp has read its outputs
+            ph_outdone ^= 1;
+            fence_after_sync();
+            out_pending = false;
+        };
         for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
             for (int t = 0; t < T; ++t) {
                 APE_TRACE(2, t, 0);
@@ -389,6 +410,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     if (!first) { mbar_wait(&bars[BAR_SLOT_FREE + c], ph_slot); fence_after_sync(); }
+                    if (c == NCH - 1 && out_pending) issue_output();             // (t == 0: the previous tile's output layer)
                     APE_TRACE(2, t, 2 + 3 * c);
                     if (elect_one()) {
                         const uint64_t wx = desc_advance(dW, c * chunk_bytes);
@@ -429,6 +451,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 if (t > 0) ph_hready ^= 1;
                 first = false;
             }
+            out_pending = a.preds != nullptr;
+        }
+        if (out_pending) {                                      // the last tile's output layer
+            mbar_wait(&bars[BAR_SLOT_FREE + NCH - 1], ph_slot);
+            fence_after_sync();
+            issue_output();
         }
     }
     __syncwarp();
@@ -438,7 +466,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 }
 
 template <int H> static size_t smem_bytes(int kgx) {
-    return 3 * (size_t)(H / 8) * ROWS * 16 + 4 * H * sizeof(float) + 128 + (size_t)(H / 32) * (kgx + H / 8) * 64 * 16;
+    return 3 * (size_t)(H / 8) * ROWS * 16 + 4 * H * sizeof(float) + BAR_BLOCK_BYTES + (size_t)(H / 32) * (kgx + H / 8) * 64 * 16;
 }
 
 template <int H> static int launch(const TcLayerArgs& a, int sm_count, cudaStream_t st) {
@@ -466,12 +494,15 @@ extern "C" int ape_lstm_tc_blob_bytes(int I, int H, int L, int64_t* bytes) {
     if (!bytes || I < 1 || H < 32 || H % 32 != 0 || L < 1) return APE_ERR_BAD_ARG;
     int64_t total = 0;
     for (int l = 0; l < L; ++l) total += (int64_t)tc_layer_bytes(l, I, H);
+    total += (int64_t)2 * (H / 8) * 16 * 16;                               // fp16 output-layer tiles: 2 CTAs x [H/8][16 columns][8] halfs
     *bytes = total;
     return APE_OK;
 }
 
 extern "C" int ape_mc_lstm_tc_supported(int I, int H, int L, int O) {
-    return ((H == 64 || H == 128 || ape::tcs::supported(H)) && L >= 2 && I >= 1 && ape_pack_kin_pad(0, I, H) <= H && O >= 1 && O <= 20) ? 1 : 0;
+    // (H <= 128: the output layer is one N = 16 tensor-core product, so O <= 16; the H = 256 kernel takes O <= 20)
+    return ((((H == 64 || H == 128) && O <= 16) || (ape::tcs::supported(H) && O <= 20)) && L >= 2 && I >= 1 &&
+            ape_pack_kin_pad(0, I, H) <= H && O >= 1) ? 1 : 0;
 }
 
 extern "C" int ape_mc_lstm_tc_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes) {
@@ -526,6 +557,8 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
 
     const int H = g->H;
     const uint8_t* wl = (const uint8_t*)g->weights_tc;
+    const uint8_t* wo16 = wl;                                               // the fp16 output-layer tile sits after all layers
+    for (int l = 0; l < g->L; ++l) wo16 += tc_layer_bytes(l, g->I, g->H);
     const float scale = g->mask_mode == APE_MASK_NONE ? 1.0f : 1.0f / (1.0f - g->dropout_p);
     for (int l = 0; l < l_end; ++l) {
         const bool last = l == g->L - 1;
@@ -563,6 +596,7 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
         a.Wo = g->weights + ape_pack_out_offset(g->I, g->H, g->L);
         a.bo = a.Wo + (size_t)g->O * g->H;
         a.O = g->O;
+        a.Wo16 = wo16;
         a.preds = last ? g->preds : nullptr;
         a.pred_ring = g->pred_ring; a.n_out = g->n_samples;
         a.cstate = scratch_region ? (float*)(scratch + (l == 0 ? 0 : scratch_region)) : nullptr;

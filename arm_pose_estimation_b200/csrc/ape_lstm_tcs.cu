@@ -389,7 +389,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 #pragma unroll
                         for (int i = 0; i < 5; ++i) acc[i] = (s + 4 * i < a.O) ? __ldg(a.bo + s + 4 * i) : 0.0f;
 #pragma unroll 2
-                        for (int g = 0; g < H / 4; ++g) {      // g = k-group * 2 + half: units 4g .. 4g+3
+                        for (int g = 0; g < (APE_EXP == 6 ? 0 : H / 4); ++g) {      // g = k-group * 2 + half: units 4g .. 4g+3 (APE_EXP 6: timing without it)
                             const float4 x = __ldcg(cst + (size_t)g * ROWS);
 #pragma unroll
                             for (int i = 0; i < 5; ++i) {
