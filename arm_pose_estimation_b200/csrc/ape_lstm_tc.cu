@@ -79,6 +79,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
     // ---- one-time set-up: weights + bias -> smem, TMEM, barriers ------------------------------------------------
+    timeline_stamp(a.timeline, 0);
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.W + (size_t)rank * w_bytes);
         uint4* dst = reinterpret_cast<uint4*>(sW);
@@ -106,6 +107,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
     cluster_sync();
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
+    timeline_stamp(a.timeline, 1);
 
     if (warp < EPI_WARPS) {
         // =================================== epilogue warps ===========================================================
@@ -272,7 +274,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                             for (int i = 0; i < 4; ++i) {      // this thread: outputs o = s, s+4, ... of its row (O <= 16)
                                 const int o = s + 4 * i;
                                 if (o < a.O && fb >= 0) {      // (an inactive stream keeps its prediction ring untouched)
-                                    const float y = __uint_as_float(o32[o]) + __uint_as_float(o32[16 + o]) + __ldg(a.bo + o);
+                                    const float y = __uint_as_float(pick4(o32, i, s)) + __uint_as_float(pick4(o32, 4 + i, s)) + __ldg(a.bo + o);
                                     float* dst = a.preds + (((size_t)b * a.pred_ring + f % a.pred_ring) * a.n_out) * a.O + o;
                                     if (a.n == 1 && a.n_out > 1) for (int s2 = 0; s2 < a.n_out; ++s2) dst[(size_t)s2 * a.O] = y;
                                     else dst[(size_t)smp * a.O] = y;
@@ -462,6 +464,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
     __syncwarp();
     fence_before_sync();
     cluster_sync();
+    timeline_stamp(a.timeline, 2);
     if (warp == MMA_WARP) tmem_dealloc<2>(tmem, TMEM_COLS);
 }
 
@@ -601,6 +604,8 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
         a.pred_ring = g->pred_ring; a.n_out = g->n_samples;
         a.cstate = scratch_region ? (float*)(scratch + (l == 0 ? 0 : scratch_region)) : nullptr;
         a.trace = (g->trace && l == g->trace_layer) ? (long long*)g->trace : nullptr;
+        // trace_layer < 0: the CTA timeline of every layer instead, [layer][TC_MAX_SMS CTAs][4]
+        a.timeline = (g->trace && g->trace_layer < 0) ? (long long*)g->trace + (size_t)l * TC_MAX_SMS * 4 : nullptr;
         rc = H == 128 ? tc::launch<128>(a, sm_count, st) : H == 64 ? tc::launch<64>(a, sm_count, st) : tcs::launch_layer(H, a, sm_count, st);
         if (rc != APE_OK) return rc;
         if (prof) APE_CUDA_TRY(cudaEventRecord(ev[l + 1], st));

@@ -41,7 +41,16 @@ struct TcLayerArgs {
     int n_pair_tiles;
     float* cstate;             // streamed-weights kernel (H = 256): per-CTA cell-state scratch, tcs::scratch_bytes() bytes
     long long* trace;          // debugging: null, or [3 roles][16 steps][16 events] SM-clock stamps of the first tile of CTA 0
+    long long* timeline;       // debugging: null, or [CTA][4] = {globaltimer at entry, after the set-up, at exit; SM id} (tools/lanes_timeline.py)
 };
+
+__device__ __forceinline__ long long globaltimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void timeline_stamp(long long* tl, int slot) {
+    if (tl && threadIdx.x == 0) {
+        tl[blockIdx.x * 4 + slot] = globaltimer_ns();
+        if (slot == 0) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); tl[blockIdx.x * 4 + 3] = sm; }
+    }
+}
 
 // Cell-update arithmetic of both tensor-core kernels.  APE_TC_TANH = 1 (default): every gate through the hardware tanh
 // (tanh.approx.f32; sigmoid(x) = 0.5 + 0.5 tanh(x / 2)) - 5 MUFU and ~10 FP32 ops per cell.  0: the exp2 / reciprocal form
@@ -52,6 +61,12 @@ struct TcLayerArgs {
 #define APE_TC_TANH 1
 #endif
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// v[4 * i + s] for a warp-uniform s in 0..3 without dynamic register indexing (which would put v in local memory)
+__device__ __forceinline__ uint32_t pick4(const uint32_t* v, int i, int s) {
+    const uint32_t a = (s & 1) ? v[4 * i + 1] : v[4 * i + 0], b = (s & 1) ? v[4 * i + 3] : v[4 * i + 2];
+    return (s & 2) ? b : a;
+}
 
 #ifndef APE_EXP
 #define APE_EXP 0            // timing experiments only (tools/tc_experiments.sh); 0 = the real kernel

@@ -190,6 +190,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
     // ---- one-time set-up: TMEM, barriers ------------------------------------------------------------------------------
+    tc::timeline_stamp(a.timeline, 0);
     if (warp == MMA_WARP) {
         tmem_alloc<2>(tmem_slot, C::TMEM_COLS);
         tmem_relinquish<2>();
@@ -214,6 +215,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
     cluster_sync();
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
+    tc::timeline_stamp(a.timeline, 1);
 
     if (warp < EPI_WARPS) {
         // =================================== epilogue warps ===========================================================
@@ -650,6 +652,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
     __syncwarp();
     fence_before_sync();
     cluster_sync();
+    tc::timeline_stamp(a.timeline, 2);
     if (warp == MMA_WARP) tmem_dealloc<2>(tmem, C::TMEM_COLS);
 }
 

@@ -99,10 +99,12 @@ class PendingEstimate:
 
 
 class BatchedEstimator:
+    N_SLOTS = 4      # staging / result buffer sets: up to N_SLOTS - 1 submitted calls may be outstanding while the next is staged
+
     def __init__(self, kind, layout, state, seq_len, y_targets, stats, n_streams, mc_samples,
                  smooth=1, dropout=0.2, bonemap=None, frames_per_call=1, emit_samples=True, normalize=True,
                  mask_mode=N.MASK_PHILOX, philox_seed=0, first_stream=0, device=None,
-                 lstm_variant="auto", tc_min_rows=1, tc_tolerance_m=5e-5, pipeline=True):
+                 lstm_variant="auto", tc_min_rows=1, tc_tolerance_m=5e-5, pipeline=True, lanes=True):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedEstimator needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = N.load()
@@ -134,7 +136,9 @@ class BatchedEstimator:
                 self.xx_m = self.xx_s = self.yy_m = self.yy_s = None
             self.body = torch.as_tensor(body_measurements_row(bonemap).astype(np.float32).ravel()).to(dev)
             self.feat_ring = ring_slots(self.nF_max, self.T)
-            self.pred_ring = ring_slots(self.nF_max, self.smooth)
+            # (two calls' worth of frames: with the two-lane pipeline the last layer of call k+1 may write its predictions
+            # while stage 3 of call k still reads the smoothing window of call k)
+            self.pred_ring = ring_slots(2 * self.nF_max, self.smooth)
             B, nF = self.B, self.nF_max
             self.raw = torch.zeros((B, nF, self.ncols), dtype=f32, device=dev)
             self.feats = torch.zeros((B, self.feat_ring, self.I), dtype=f32, device=dev)
@@ -142,19 +146,20 @@ class BatchedEstimator:
             # results live in ONE device buffer [msg | std | status | samples] so a full call leaves in one D2H copy
             E = B * nF
             n_words = E * (25 + 6 + 1) + (E * self.S * 6 if emit_samples else 0)
-            # (two of them: the D2H copy of call k runs on a side stream under the kernels of call k+1)
-            self.out_bufs = [torch.zeros(n_words, dtype=f32, device=dev) for _ in range(2)]
+            # (N_SLOTS of them: the D2H copy of call k runs on a side stream under the kernels of the calls after it)
+            NS = self.N_SLOTS
+            self.out_bufs = [torch.zeros(n_words, dtype=f32, device=dev) for _ in range(NS)]
             self.copy_stream = torch.cuda.Stream(device=dev)
-            self.copy_done = [None, None]
+            self.copy_done = [None] * NS
             self._use_out(0)
             # sized for the largest call; a shorter call re-tiles its rows, so leave one tile of slack per buffer
             ws_bytes = N.workspace_bytes(self.I, self.H, self.L, self.T, self.O, B * nF, self.n) + 3 * 64 * self.T * self.H * 4
             self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            # pinned staging for the host-facing calls: two slots, so call k+1 can be staged and enqueued while the
+            # pinned staging for the host-facing calls: N_SLOTS slots, so the next calls can be staged and enqueued while the
             # results of call k are still on their way back (submit() / PendingEstimate.result())
-            self.raw_host = [torch.zeros((B, nF, self.ncols), dtype=f32).pin_memory() for _ in range(2)]
-            self.out_host = [torch.zeros(n_words, dtype=f32).pin_memory() for _ in range(2)]
-            self.slot_event = [None, None]
+            self.raw_host = [torch.zeros((B, nF, self.ncols), dtype=f32).pin_memory() for _ in range(NS)]
+            self.out_host = [torch.zeros(n_words, dtype=f32).pin_memory() for _ in range(NS)]
+            self.slot_event = [None] * NS
             self.frames_host = self.frames_dev = None      # per-stream frame counters (multi-stream front-end), made on first use
             self.submits = 0
             # ---- which LSTM kernel: fp32 FFMA (exact) or tcgen05 fp16-operand tensor cores ----------------------
@@ -178,11 +183,21 @@ class BatchedEstimator:
                 self.tc_probe_error_m = self._probe_tc_error()
                 if lstm_variant == "tc" or self.tc_probe_error_m <= tc_tolerance_m:
                     self.lstm_variant = "tc"
-            # cross-call software pipeline (tensor-core path): stage 1 + LSTM layer 0 of call k+1 (a few dozen CTAs) run on a
-            # side stream under the tail of call k's big layer kernels; layer 0's output is double-buffered by call parity
+            # cross-call software pipeline (tensor-core path), two levels:
+            #  * stage 1 + LSTM layer 0 of call k+1 (a few dozen CTAs) run on a side stream under call k's big layer kernels;
+            #    layer 0's output is double-buffered by call parity;
+            #  * the big layer kernels (persistent, one CTA pair per SM pair, a whole number of 256-row tiles per pair) and stage 3
+            #    of consecutive calls go to two alternating "lane" streams with a workspace each: a layer's last round of tiles
+            #    fills only part of the GPU (400 tiles over 74 pairs = 5.4 rounds), and the pairs that finish early pick up the
+            #    next call's layer instead of idling until the launch drains.  At most two calls are in flight.
             self.pipeline = bool(pipeline) and self.lstm_variant == "tc"
-            self.side_stream = torch.cuda.Stream(device=dev) if self.pipeline else None
-            self.l1_done = [None, None]
+            # (high priority: its few dozen CTAs take the first SMs any big launch frees, so layer 0 is ready well before its call's turn)
+            self.side_stream = torch.cuda.Stream(device=dev, priority=-1) if self.pipeline else None
+            self.lanes = bool(lanes) and self.pipeline
+            self.lane_streams = [torch.cuda.Stream(device=dev) for _ in range(2)] if self.lanes else None
+            self.lane_ws = [self.workspace, torch.empty_like(self.workspace)] if self.lanes else None
+            self.l1_done = [None] * 4             # completion of the last call that used buffer set (call & 3)
+            self.lstm_done = None             # last LSTM layer of the previous call (its predictions feed this call's smoothing window)
         self.calls = 0
         self.frame = 0
         self.launches = 0             # kernels launched so far (bench.py reports it)
@@ -236,7 +251,7 @@ class BatchedEstimator:
 
     # ---- device path -----------------------------------------------------------------------------------
     def step_device(self, raw, n_frames=None, masks=None, layer_ms=None, trace=None, trace_layer=1, raw_ready=False,
-                    _h2d_from=None, stream_frames=None, _frames_from=None):
+                    _h2d_from=None, stream_frames=None, _frames_from=None, _out_slot=None, timeline=None):
         """``raw``: device tensor ``[B, nF, ncols]`` float32 (nF <= frames_per_call).  Enqueues the three stages and returns an
         ``EstimateBatch`` of views into the estimator's device buffers (valid until the call after next).  ``raw_ready=True``
         promises that ``raw`` is already materialised (not pending on the current stream), which lets the pipelined path
@@ -277,20 +292,42 @@ class BatchedEstimator:
             a.layer_ms = layer_ms.ctypes.data
         if trace is not None:                        # debugging: device int64[768] of SM-clock stamps (tensor-core path)
             a.trace, a.trace_layer = trace.data_ptr(), trace_layer
+        if timeline is not None:                     # debugging: device int64[L, 160, 4] CTA timeline (does not leave the pipelined path)
+            a.trace, a.trace_layer = timeline.data_ptr(), -1
 
         def features(stream_ptr):
             N.check(lib.ape_features(N.ptr(raw), self.layout, self.kind, N.ptr(self.xx_m), N.ptr(self.xx_s),
                                      1 if self.normalize else 0, N.ptr(self.feats), B, nF, frame0, N.ptr(sf), self.feat_ring, stream_ptr),
                     "ape_features")
 
+        def stage3(stream_ptr):
+            N.check(lib.ape_fk_reduce(N.ptr(self.preds), self.pred_ring, N.ptr(self.yy_m), N.ptr(self.yy_s), N.ptr(self.body),
+                                      self.target, self.O, B, nF, frame0, N.ptr(sf), self.n, self.smooth,
+                                      N.ptr(self.msg), N.ptr(self.samples), N.ptr(self.std), None, N.ptr(self.status), stream_ptr),
+                    "ape_fk_reduce")
+
         if self.pipeline and layer_ms is None and trace is None:
+            # buffer set of this call: lane (stream + workspace) = call & 1; with lanes each workspace's two copies of layer 0's
+            # output alternate as well, so stage 1 + layer 0 may run up to three calls ahead of the big kernels (whichever
+            # launch's tail has room for their few dozen CTAs) and never gate the next call's first big layer
             side, parity = self.side_stream, self.calls & 1
-            if not raw_ready and _h2d_from is None:
+            bufset = self.calls & 3 if self.lanes else parity
+            lane = self.lane_streams[parity] if self.lanes else main      # (lanes off: the big kernels stay on the caller's stream)
+            if self.lanes:
+                a.workspace = self.lane_ws[parity].data_ptr()
+            if _out_slot is None:
+                self._use_out(self.calls % self.N_SLOTS)     # results of call k stay valid while the next calls are computed
+            # inputs the caller may still have pending on its own stream (everything but the staged host-facing path)
+            if (not raw_ready and _h2d_from is None) or md is not None or (sf is not None and _frames_from is None):
                 ev_in = torch.cuda.Event()
                 ev_in.record(main)
-                side.wait_event(ev_in)               # raw may still be pending on the caller's stream
-            if self.l1_done[parity] is not None:
-                side.wait_event(self.l1_done[parity])    # layer 1 of call k-2 has finished reading this copy of layer 0's output
+                side.wait_event(ev_in)
+                if self.lanes:
+                    lane.wait_event(ev_in)
+                if md is not None and self.lanes:
+                    md.record_stream(lane)           # (allocated on the caller's stream, read by the lane's kernels)
+            if self.l1_done[bufset] is not None:
+                side.wait_event(self.l1_done[bufset])    # the last call on this buffer set (layer 0's output, frames) has finished
             with torch.cuda.stream(side):
                 if _h2d_from is not None:
                     raw.copy_(_h2d_from, non_blocking=True)
@@ -298,17 +335,27 @@ class BatchedEstimator:
                     sf.copy_(_frames_from, non_blocking=True)
                 sp = C_void(side.cuda_stream)
                 features(sp)
-                a.layer_begin, a.layer_end, a.ws_parity = 0, 1, parity
+                a.layer_begin, a.layer_end, a.ws_parity = 0, 1, (bufset >> 1) if self.lanes else parity
                 N.check(lib.ape_mc_lstm_tc(a, sp), "ape_mc_lstm_tc (layer 0)")
                 ev0 = torch.cuda.Event()
                 ev0.record(side)
-            main.wait_event(ev0)
-            st = N.current_stream_ptr()
-            a.layer_begin, a.layer_end = 1, self.L
-            N.check(lib.ape_mc_lstm_tc(a, st), "ape_mc_lstm_tc (layers >= 1)")
-            ev1 = torch.cuda.Event()
-            ev1.record(main)
-            self.l1_done[parity] = ev1
+            lane.wait_event(ev0)
+            if self.copy_done[self.out_slot] is not None:
+                lane.wait_event(self.copy_done[self.out_slot])   # this output buffer has been read back (submit(), call k-2)
+            with torch.cuda.stream(lane):
+                lp = C_void(lane.cuda_stream)
+                a.layer_begin, a.layer_end = 1, self.L
+                N.check(lib.ape_mc_lstm_tc(a, lp), "ape_mc_lstm_tc (layers >= 1)")
+                if self.lstm_done is not None:
+                    lane.wait_event(self.lstm_done)      # the smoothing window reaches into the previous call's predictions
+                self.lstm_done = torch.cuda.Event()
+                self.lstm_done.record(lane)
+                stage3(lp)
+                done = torch.cuda.Event()
+                done.record(lane)
+            self.l1_done[bufset] = done
+            if self.lanes:
+                main.wait_event(done)                    # the caller's stream sees the results, as without the lanes
         else:
             if _h2d_from is not None:
                 raw.copy_(_h2d_from, non_blocking=True)
@@ -317,10 +364,7 @@ class BatchedEstimator:
             st = N.current_stream_ptr()
             features(st)
             N.check(self._lstm_fn()(a, st), "ape_mc_lstm")
-        N.check(lib.ape_fk_reduce(N.ptr(self.preds), self.pred_ring, N.ptr(self.yy_m), N.ptr(self.yy_s), N.ptr(self.body),
-                                  self.target, self.O, B, nF, frame0, N.ptr(sf), self.n, self.smooth,
-                                  N.ptr(self.msg), N.ptr(self.samples), N.ptr(self.std), None, N.ptr(self.status), st),
-                "ape_fk_reduce")
+            stage3(st)
         self.launches += 2 + self.L
         self.calls += 1
         out = EstimateBatch(self._view(self.msg, nF), self._view(self.std, nF), self._view(self.samples, nF),
@@ -339,7 +383,7 @@ class BatchedEstimator:
     def submit(self, rows, masks=None, stream_frames=None):
         """Stage ``rows`` (host array ``[B, nF, ncols]`` or ``[B, ncols]`` of float32 wire rows) in pinned memory and
         enqueue H2D copy -> the three stages -> D2H copy on the current stream WITHOUT waiting.  Returns a
-        ``PendingEstimate``; at most two may be outstanding (two staging slots).  ``stream_frames``: optional host int32
+        ``PendingEstimate``; a slot is reused after ``N_SLOTS`` calls (the call then first waits for that slot's results to land).  ``stream_frames``: optional host int32
         array ``[B]`` of per-stream frame numbers (negative: the stream has no new row in this call), see ``step_device``."""
         rows = np.asarray(rows, dtype=np.float32)
         if rows.ndim == 2:
@@ -347,7 +391,7 @@ class BatchedEstimator:
         nF = rows.shape[1]
         if rows.shape[0] != self.B or nF > self.nF_max or rows.shape[2] != self.ncols:
             raise UserWarning(f"rows must be [B={self.B}, nF<={self.nF_max}, {self.ncols}], got {rows.shape}")
-        slot = self.submits % 2
+        slot = self.submits % self.N_SLOTS
         self.submits += 1
         if self.slot_event[slot] is not None:
             self.slot_event[slot].synchronize()           # the slot's previous results have landed; its staging is free
@@ -363,11 +407,11 @@ class BatchedEstimator:
             sf_dev = sf_host = None
             if stream_frames is not None:
                 if self.frames_host is None:
-                    self.frames_host = [torch.zeros(self.B, dtype=torch.int32).pin_memory() for _ in range(2)]
-                    self.frames_dev = [torch.zeros(self.B, dtype=torch.int32, device=self.device) for _ in range(2)]
-                sf_host, sf_dev = self.frames_host[slot], self.frames_dev[slot]
+                    self.frames_host = [torch.zeros(self.B, dtype=torch.int32).pin_memory() for _ in range(self.N_SLOTS)]
+                    self.frames_dev = [torch.zeros(self.B, dtype=torch.int32, device=self.device) for _ in range(4)]
+                sf_host, sf_dev = self.frames_host[slot], self.frames_dev[self.calls & 3]     # (device copies: one per buffer set)
                 sf_host.numpy()[...] = np.asarray(stream_frames, dtype=np.int32).reshape(self.B)
-            out = self.step_device(raw, nF, masks, _h2d_from=stage, stream_frames=sf_dev, _frames_from=sf_host)
+            out = self.step_device(raw, nF, masks, _h2d_from=stage, stream_frames=sf_dev, _frames_from=sf_host, _out_slot=slot)
             computed = torch.cuda.Event()
             computed.record(main)
             host, dev_out = self.out_host[slot], self.out_all
@@ -395,7 +439,7 @@ class BatchedEstimator:
 
     def step(self, rows, masks=None, stream_frames=None):
         """``submit`` + wait.  Returns an ``EstimateBatch`` of HOST arrays (views of a pinned staging slot, valid until
-        the slot is reused two calls later)."""
+        the slot is reused ``N_SLOTS`` calls later)."""
         return self.submit(rows, masks, stream_frames).result()
 
     @property

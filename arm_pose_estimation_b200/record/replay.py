@@ -115,7 +115,7 @@ def pad_recordings(recordings):
 def relabel_recordings(recordings, make_estimator, frames_per_call=16, keep_samples=False):
     """Offline relabelling: ``recordings`` = list of ``[frames_i, ncols]`` arrays (or one ``[R, F, ncols]`` array);
     ``make_estimator(n_streams, frames_per_call)`` returns a ``BatchedEstimator``.  Returns a list of dicts with
-    ``msg [frames_i, 25]``, ``std [frames_i, 6]`` (and ``samples`` if asked).  Call k+1 is staged while call k runs."""
+    ``msg [frames_i, 25]``, ``std [frames_i, 6]`` (and ``samples`` if asked).  The next calls are staged and enqueued while call k runs."""
     if isinstance(recordings, np.ndarray) and recordings.ndim == 3:
         rows, lengths = np.asarray(recordings, dtype=np.float32), np.full(len(recordings), recordings.shape[1], np.int64)
     else:
@@ -137,14 +137,14 @@ def relabel_recordings(recordings, make_estimator, frames_per_call=16, keep_samp
         if keep_samples:
             samples[:, f0:f0 + nf] = out.samples
 
-    prev = None
+    outstanding = []                                          # submitted, not yet collected (oldest first)
     for f0 in range(0, F, be.nF_max):
         nf = min(be.nF_max, F - f0)
-        cur = (be.submit(rows[:, f0:f0 + nf]), f0, nf)
-        if prev is not None:
-            collect(*prev)
-        prev = cur
-    collect(*prev)
+        outstanding.append((be.submit(rows[:, f0:f0 + nf]), f0, nf))
+        if len(outstanding) >= be.N_SLOTS - 1:                # the next submit reuses the oldest one's staging slot
+            collect(*outstanding.pop(0))
+    for item in outstanding:
+        collect(*item)
     res = []
     for i in range(R):
         d = dict(msg=msg[i, : lengths[i]].astype(np.float64), std=std[i, : lengths[i]].astype(np.float64))

@@ -118,7 +118,9 @@ typedef struct ape_lstm_args {
        on a second stream under the tail of this call; ws_parity (0 | 1) selects one of two copies of layer 0's output */
     int layer_begin, layer_end, ws_parity;
     /* debugging (tensor-core path): null, or a device buffer of 768 int64 that receives SM-clock stamps of the first
-       tile of CTA 0 of layer `trace_layer` ([role: epilogue, loader, issuer][step < 16][event < 16]) */
+       tile of CTA 0 of layer `trace_layer` ([role: epilogue, loader, issuer][step < 16][event < 16]; needs a library built
+       with -DAPE_TC_TRACE=1).  trace_layer < 0: instead the CTA timeline of every layer, a device buffer of [L][160 CTAs][4]
+       int64 = {globaltimer ns at entry, after the set-up, at exit; SM id} (tools/lanes_timeline.py) */
     void* trace;
     int trace_layer;
     /* per-stream frame counters [B] on the device (null: every stream is at frame0); < 0: skip the stream */
