@@ -108,6 +108,36 @@ __device__ __forceinline__ uint4 philox_keep_halfmask(uint64_t seed, uint32_t st
 }
 #endif
 
+// Philox4x32-10's key schedule depends on the seed alone: the host evaluates the 10 round keys once and passes them as kernel
+// parameters, so on the device they are constant-bank / uniform-register operands of the round's XORs - a round is then
+// 2 IMAD.WIDE + 2 LOP3 instead of 8 issue slots (the tensor-core kernels' loader warps are issue-bound).
+struct PhiloxRoundKeys { uint32_t k[20]; };
+APE_HD PhiloxRoundKeys philox_round_keys(uint64_t seed) {
+    PhiloxRoundKeys rk;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { rk.k[2 * r] = k0; rk.k[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return rk;
+}
+#ifdef __CUDACC__
+// philox_keep_halfmask with precomputed round keys: bit-identical draws
+__device__ __forceinline__ uint4 philox_keep_halfmask_rk(const PhiloxRoundKeys& rk, uint32_t stream, uint32_t frame, uint32_t sample,
+                                                         uint32_t gap, uint32_t t, uint32_t group, uint32_t keep_thr16) {
+    if (keep_thr16 >= 65536u) return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint32_t c0 = stream, c1 = frame, c2 = (sample & 0xFFFFFu) | ((gap & 0xFu) << 20) | ((t & 0xFFu) << 24), c3 = group;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(M0, c0, hi0, lo0);
+        mulhilo32(M1, c2, hi1, lo1);
+        const uint32_t n0 = hi1 ^ c1 ^ rk.k[2 * r], n2 = hi0 ^ c3 ^ rk.k[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    const uint32_t thr2 = keep_thr16 | (keep_thr16 << 16);
+    return make_uint4(__vcmpltu2(c0, thr2), __vcmpltu2(c1, thr2), __vcmpltu2(c2, thr2), __vcmpltu2(c3, thr2));
+}
+#endif
+
 APE_HD uint32_t keep_threshold16(float p) {
     float k = (1.0f - p) * 65536.0f + 0.5f;
     return k >= 65536.0f ? 65536u : (k <= 0.0f ? 0u : (uint32_t)k);

@@ -29,7 +29,10 @@
 namespace ape {
 namespace tc {
 
-constexpr int EPI_WARPS = 16, LOAD_WARPS = 8;
+#ifndef APE_TC_LOAD_WARPS
+#define APE_TC_LOAD_WARPS 8
+#endif
+constexpr int EPI_WARPS = 16, LOAD_WARPS = APE_TC_LOAD_WARPS;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS;
 constexpr int THREADS = (MMA_WARP + 1) * 32;       // 16 epilogue + 8 operand-loader + 1 MMA-issue warps = 800
@@ -291,7 +294,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
         }
     } else if (warp < MMA_WARP) {
         // =================================== operand-loader warps: x_t -> sAx ===========================================
-        const int row_l = (tid - EPI_THREADS) & (ROWS - 1);    // two threads per row, each half of the x k-groups
+        constexpr int TPR = LOAD_WARPS * 32 / ROWS;            // loader threads per row, each an equal share of the x k-groups
+        const int row_l = (tid - EPI_THREADS) & (ROWS - 1);
         const int half = (tid - EPI_THREADS) >> 7;
         uint32_t ph_xdone = 0;
         bool first = true;
@@ -309,7 +313,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     else src += ((((size_t)(e >> (a.in_rpc_shift + 1)) * T + t) * 2 + ((e >> a.in_rpc_shift) & 1)) * KG) * ROWS +
                                 (e & ((1 << a.in_rpc_shift) - 1));
                     if (warp == EPI_WARPS) APE_TRACE(1, t, 0);
-                    constexpr int KH = KG / 2;
+                    constexpr int KH = KG / TPR;
                     const int j0 = half * KH;
                     src += (size_t)j0 * ROWS;
                     uint4 pre[KH];
@@ -319,7 +323,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     for (int jj = 0; jj < KH; ++jj) {
                         const int j = j0 + jj;
                         if (a.mask_mode == APE_MASK_PHILOX && APE_EXP != 3) {
-                            const uint4 m = philox_keep_halfmask(a.seed, a.stream_id0 + (uint32_t)b, (uint32_t)f, (uint32_t)smp,
+                            const uint4 m = APE_PHILOX_DRAW(a, a.stream_id0 + (uint32_t)b, (uint32_t)f, (uint32_t)smp,
                                                                  (uint32_t)a.gap, (uint32_t)t, (uint32_t)j, a.keep_thr16);
                             pre[jj].x &= m.x; pre[jj].y &= m.y; pre[jj].z &= m.z; pre[jj].w &= m.w;
                         } else if (a.mask_mode == APE_MASK_INJECTED && valid) {
@@ -350,7 +354,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                             src = reinterpret_cast<const float*>(a.in) + ((size_t)b * a.feat_ring + fw % a.feat_ring) * a.Kin;
                         }
                     }
-                    for (int j = half; j < kgx; j += 2) {
+                    for (int j = half; j < kgx; j += TPR) {
                         float v[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) v[k] = (valid && 8 * j + k < a.Kin) ? __ldg(src + 8 * j + k) : 0.0f;
@@ -594,6 +598,7 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
         }
         a.masks = g->masks; a.gap = l - 1; a.n_gaps = g->L - 1;
         a.seed = g->philox_seed; a.stream_id0 = g->stream_id0;
+        a.rk = philox_round_keys(g->philox_seed);
         a.keep_thr16 = keep_threshold16(g->dropout_p);
         a.out_scale = scale;                                            // the next layer's dropout scale, applied before rounding
         a.Wo = g->weights + ape_pack_out_offset(g->I, g->H, g->L);

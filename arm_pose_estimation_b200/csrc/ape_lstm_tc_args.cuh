@@ -27,6 +27,7 @@ struct TcLayerArgs {
     const uint8_t* masks;
     int gap, n_gaps;
     uint64_t seed;
+    PhiloxRoundKeys rk;        // philox_round_keys(seed)
     uint32_t stream_id0;
     uint32_t keep_thr16;
     uint4* out_units;          // [pair tile][T][cta][k-group][128 rows] 16-byte units of fp16 (h_t * out_scale), or null
@@ -67,6 +68,15 @@ __device__ __forceinline__ uint32_t pick4(const uint32_t* v, int i, int s) {
     const uint32_t a = (s & 1) ? v[4 * i + 1] : v[4 * i + 0], b = (s & 1) ? v[4 * i + 3] : v[4 * i + 2];
     return (s & 2) ? b : a;
 }
+
+#ifndef APE_PHILOX_RK
+#define APE_PHILOX_RK 1      // 1: host-evaluated Philox round keys (constant-bank operands); 0: key schedule on the device (A/B only)
+#endif
+#if APE_PHILOX_RK
+#define APE_PHILOX_DRAW(a, ...) philox_keep_halfmask_rk((a).rk, __VA_ARGS__)
+#else
+#define APE_PHILOX_DRAW(a, ...) philox_keep_halfmask((a).seed, __VA_ARGS__)
+#endif
 
 #ifndef APE_EXP
 #define APE_EXP 0            // timing experiments only (tools/tc_experiments.sh); 0 = the real kernel

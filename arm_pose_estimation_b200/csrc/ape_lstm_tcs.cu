@@ -459,7 +459,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         if (a.mask_mode == APE_MASK_PHILOX) {
 #pragma unroll
                             for (int jj = 0; jj < BK; ++jj) {
-                                const uint4 m = philox_keep_halfmask(a.seed, stream, (uint32_t)f, (uint32_t)smp, (uint32_t)a.gap, (uint32_t)t,
+                                const uint4 m = APE_PHILOX_DRAW(a, stream, (uint32_t)f, (uint32_t)smp, (uint32_t)a.gap, (uint32_t)t,
                                                                      (uint32_t)(j0 + b0 + jj), a.keep_thr16);
                                 pre[jj].x &= m.x; pre[jj].y &= m.y; pre[jj].z &= m.z; pre[jj].w &= m.w;
                             }
@@ -551,7 +551,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         }
                         // the piece is in BOTH CTAs' rings (one slot, or two consecutive ones for > 8 MMAs): one barrier per piece
                         uint32_t spins = 0;
-                        while (!mbar_try_wait_addr(bar_full + (gpiece & (C::NFULL - 1)) * 8, (gpiece / C::NFULL) & 1)) { if (++spins > (1u << 24)) __trap(); }
+                        while (!mbar_try_wait_addr(bar_full + (gpiece & (C::NFULL - 1)) * 8, (gpiece / C::NFULL) & 1)) { if (++spins > MBAR_WD_SPINS) __trap(); }
                         // LAST, because it is what the step boundary waits for: the K-slices of h_{t-1} this piece multiplies have
                         // been published.  Every epilogue warp publishes its slices in order, so slice k complete implies k-1, ...
                         const uint32_t hneed = (e.x >> E_HNEED_SHIFT) & 0xF;
