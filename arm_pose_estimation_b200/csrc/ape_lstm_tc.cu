@@ -501,7 +501,7 @@ extern "C" int ape_lstm_tc_blob_bytes(int I, int H, int L, int64_t* bytes) {
     if (!bytes || I < 1 || H < 32 || H % 32 != 0 || L < 1) return APE_ERR_BAD_ARG;
     int64_t total = 0;
     for (int l = 0; l < L; ++l) total += (int64_t)tc_layer_bytes(l, I, H);
-    total += (int64_t)2 * (H / 8) * 16 * 16;                               // fp16 output-layer tiles: 2 CTAs x [H/8][16 columns][8] halfs
+    total += (int64_t)2 * (H / 8) * (H > 128 ? 32 : 16) * 16;              // fp16 output-layer tiles: 2 CTAs x [H/8][16 | 32 (H = 256) columns][8] halfs
     *bytes = total;
     return APE_OK;
 }

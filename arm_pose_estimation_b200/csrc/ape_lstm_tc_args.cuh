@@ -34,8 +34,8 @@ struct TcLayerArgs {
     float out_scale;           // the consumer's 1/(1-p): scaling BEFORE the fp16 rounding keeps it a single rounding
     const float* Wo;
     const float* bo;
-    const uint8_t* Wo16;       // fp16 output-layer tiles [cta 2][H/8 k-groups][16 outputs][8 halfs]: cta 0 fp16(W_o), cta 1 the remainder
-                               // W_o - fp16(W_o) as fp16 (outputs >= O are zero rows)
+    const uint8_t* Wo16;       // fp16 output-layer tiles [cta 2][H/8 k-groups][16 outputs (H = 256: 32)][8 halfs]: cta 0 fp16(W_o),
+                               // cta 1 the remainder W_o - fp16(W_o) as fp16 (outputs >= O are zero rows)
     int O;
     float* preds;
     int pred_ring, n_out;

@@ -15,8 +15,10 @@
 //     Only x_t (streamed in by the loader warps, dropout applied on the way) is a shared-memory operand tile.
 //   * The fp32 CELL STATE c (64 values per epilogue thread - too many for the register file next to the epilogue's
 //     working set) lives in a per-CTA 128 KB scratch in global memory that never leaves L2: each thread prefetches the
-//     4 values of its next half-pass while it computes the current one (coalesced 512 B per warp and access).  On the
-//     last step of the last layer the same scratch carries h_T in fp32 to the output layer.
+//     4 values of its next half-pass while it computes the current one (coalesced 512 B per warp and access).
+//   * The OUTPUT LAYER of the last layer is one more tensor-core product: h_T stays in TMEM like every other h_t and is multiplied
+//     by [fp16(W_o) | W_o - fp16(W_o)]^T (one extra 16 KB ring piece, N = 64) into accumulator slot 1 where that slot would be
+//     refilled for the next tile; the epilogue sums the two halves (W_o enters with ~22 bits) and adds the bias.
 //   * Schedule: chunk 0 of step t+1 is issued into its slot as soon as the epilogue of step t has drained chunk NCH - 2
 //     from it - the x-part, then the recurrent K-slices already published - and chunk 1's x-part follows when chunk
 //     NCH - 1 is drained, so when the last slice of h_t lands only one small piece (2 MMAs) stands between it and the first
@@ -79,10 +81,13 @@ template <int H> struct Cfg {
     static constexpr uint32_t H_COLS = H / 2;                         // fp16 pairs: one buffer
     static constexpr uint32_t TMEM_COLS = 512;
     static constexpr size_t CSTATE_BYTES = (size_t)H * ROWS * 4;      // per-CTA cell-state scratch (global, L2-resident)
+    static constexpr uint32_t OUT_N = 64;                             // output product: 32 outputs x {fp16(W_o), remainder}
+    static constexpr uint32_t OUT_BYTES = KG * (OUT_N / 2) * 16;      // this CTA's tile of it: one ring slot
+    static_assert(OUT_BYTES <= SLOT_BYTES, "the output-layer tile must fit a ring slot");
     enum {
         BAR_X_READY = 0, BAR_X_DONE = 2, BAR_ACC_READY = 4, BAR_SLOT_FREE = BAR_ACC_READY + NSLOT,
         BAR_H_READY = BAR_SLOT_FREE + NSLOT, BAR_W_FULL = BAR_H_READY + NCH, BAR_W_EMPTY = BAR_W_FULL + NFULL,
-        BAR_COUNT = BAR_W_EMPTY + NP
+        BAR_OUT_READY = BAR_W_EMPTY + NP, BAR_OUT_DONE = BAR_OUT_READY + 1, BAR_COUNT = BAR_OUT_DONE + 1
     };
     static_assert(NSLOT == 2 && NCH % 2 == 0 && NCH > NSLOT, "chunks alternate between the two accumulator slots");
     static_assert(H_COL + 2 * H_COLS <= TMEM_COLS, "accumulator slots + two h buffers must fit the 512 TMEM columns");
@@ -95,6 +100,8 @@ template <int H> struct Cfg {
 //   piece(c, is_h, kg0, nkg, first)     chunk c (+)= A[:, k-groups kg0 .. kg0+nkg) x W_c[k-groups]^T  (x-part or recurrent part);
 //                                       a recurrent piece needs the K-slices (of SLICE_KG k-groups) it covers published
 //   acc_done(c) / x_done()              chunk c complete / this slot's share of the x tile has been consumed
+//   out_point()                         (first step of a tile) before the next piece: the output layer of the PREVIOUS tile, one
+//                                       extra ring piece (the W_o tile) multiplied by that tile's h_T into accumulator slot 1
 template <int NCH, class V>
 static void walk_step(bool first_step, int kgx, V& v) {
     const int KG = NCH * SLICE_KG;
@@ -104,6 +111,7 @@ static void walk_step(bool first_step, int kgx, V& v) {
     };
     for (int c = 0; c < NCH; ++c) {
         v.chunk_begin(c);
+        if (first_step && c == 1) v.out_point();               // slot 1 is free and the previous tile's h_T is complete by now
         range(c, false, 0, kgx, true);
         if (c >= NCH - NSLOT) v.x_done();                      // the last x-part of each accumulator slot (= of each issuer)
         if (first_step) {                                      // h_{-1} = 0: no recurrent half
@@ -136,6 +144,7 @@ enum : uint32_t {
     E_PRE_SLOT = 1u << 3,     // before: wait until the epilogue has drained this slot
     E_POST_ACC = 1u << 4,     // after: the chunk is complete
     E_POST_X = 1u << 5,       // after: the x tile has been consumed
+    E_OUT_BEFORE = 1u << 6,   // before (and before the slot wait's refill): the previous tile's output-layer piece, if there is one
     E_NMMA_SHIFT = 8,         // [8, 13)   K=16 MMAs in the piece (1..16)
     E_HNEED_SHIFT = 13,       // [13, 17)  K-slices of h_{t-1} that must have been published (0..NCH)
     E_SRC_SHIFT = 17          // [17, 32)  k-group offset of the piece inside this CTA's weight tiles (1 KB units)
@@ -153,6 +162,7 @@ struct Recorder {
     uint32_t pre;
     bool overflow;
     void chunk_begin(int) { pre |= E_PRE_SLOT; }
+    void out_point() { pre |= E_OUT_BEFORE; }
     void piece(int c, bool is_h, int kg0, int nkg, bool first) {
         if (n >= MAX_ENTRIES) { overflow = true; return; }
         const uint32_t src_kg = (uint32_t)c * (uint32_t)(kgx + KG) + (is_h ? (uint32_t)kgx : 0u) + (uint32_t)kg0;
@@ -208,6 +218,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
         // leader: its own copy (arrive.expect_tx + bytes) and the peer's "my copy landed" arrival; peer: its own copy
         for (int p = 0; p < C::NFULL; ++p) mbar_init(&bars[C::BAR_W_FULL + p], rank == 0 ? 2 : 1);
         for (int p = 0; p < NP; ++p) mbar_init(&bars[C::BAR_W_EMPTY + p], 1);
+        mbar_init(&bars[C::BAR_OUT_READY], 1);
+        mbar_init(&bars[C::BAR_OUT_DONE], 2 * EPI_WARPS);
         mbar_init_fence();
     }
     fence_proxy_async_smem();
@@ -226,7 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
         const bool warp_live = 32 * q < a.rpc;                 // a quarter without rows only keeps the barrier protocol going
         // this thread's cell state: float4 (4 units) per half-pass at [(k-group j = 4c + s) * 2 + half][row]
         float4* cst = reinterpret_cast<float4*>(a.cstate + (size_t)blockIdx.x * (C::CSTATE_BYTES / 4)) + row_l;
-        uint32_t gstep = 0;
+        uint32_t gstep = 0, ph_out = 0;
 
         for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
             const int row = (tile * 2 + (int)rank) * a.rpc + row_l;
@@ -243,7 +255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         mbar_wait_wd(&bars[C::BAR_ACC_READY + (c & 1)], par0 ^ ((c >> 1) & 1));
                         if (lane == 0) {
                             mbar_arrive_leader(&bars[C::BAR_SLOT_FREE + (c & 1)], rank);
-                            if (t + 1 < T) mbar_arrive_leader(&bars[C::BAR_H_READY + c], rank);
+                            if (t + 1 < T || final_out) mbar_arrive_leader(&bars[C::BAR_H_READY + c], rank);
                         }
                     }
                 } else {
@@ -352,16 +364,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 #pragma unroll
                         for (int u = 0; u < 4; ++u) hv[u] = (1.0f - num[u]) * rcp_approx((1.0f + ev[4 * u + 3]) * (1.0f + num[u]));
 #endif
-                        // cell state back to its scratch line (not needed after the last step); on the last step of the last
-                        // layer the line carries h_T (fp32) to the output layer instead
-                        if (final_out) __stcg(cst + (size_t)((4 * c + s) * 2 + half) * ROWS, make_float4(hv[0], hv[1], hv[2], hv[3]));
-                        else if (t + 1 < T && APE_EXP != 8) __stcg(cst + (size_t)((4 * c + s) * 2 + half) * ROWS, make_float4(cn[0], cn[1], cn[2], cn[3]));
+                        // cell state back to its scratch line (not needed after the last step)
+                        if (t + 1 < T && APE_EXP != 8) __stcg(cst + (size_t)((4 * c + s) * 2 + half) * ROWS, make_float4(cn[0], cn[1], cn[2], cn[3]));
                         const int j = 4 * c + s;               // k-group of units 32c + 8s .. + 7
                         if (half == 1) {
-                            if (t + 1 < T) {
+                            if (t + 1 < T || final_out) {
                                 // h_t as fp16 pairs into the TMEM operand buffer of the next step (lane = row, 4 columns = this
                                 // k-group), then publish this chunk's K-slice: its piece of the next recurrent product can be
-                                // issued while later chunks still run
+                                // issued while later chunks still run (last step of the last layer: h_T feeds the output product)
                                 if (APE_EXP != 9) {
                                 tmem_st_x4(tmem + t_lane + h_next + (uint32_t)(4 * j), pack_half2(hlo[0], hlo[1]), pack_half2(hlo[2], hlo[3]),
                                            pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]));
@@ -384,39 +394,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     }
                 }
                 if (final_out) {                               // output_layer (nn_models.py:189), last step only
-                    epi_bar_sync();                            // h_T of all 4 unit groups of every row is in the scratch
+                    // Issuer 1 multiplies the published h_T (TMEM) by [fp16(W_o) | W_o - fp16(W_o)]^T - one extra ring piece - into
+                    // the first 64 columns of accumulator slot 1 once chunk NCH-1 has been drained from it.  Every warp waits for
+                    // the product: that is also the guarantee that h_T has been consumed before the next tile rewrites the buffer.
+                    mbar_wait_wd(&bars[C::BAR_OUT_READY], ph_out);
+                    ph_out ^= 1;
+                    fence_after_sync();
                     if (warp_live) {
-                        // this thread: outputs o = s, s+4, ... of its row (<= 5 for O <= 20), one sweep over the H values of h_T
-                        float acc[5];
+                        uint32_t v[32];
+                        float y[8];
+                        tmem_ld_x32(tmem + t_lane + 128u, v);                  // h_T x fp16(W_o)^T, outputs 0..31
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) acc[i] = (s + 4 * i < a.O) ? __ldg(a.bo + s + 4 * i) : 0.0f;
-#pragma unroll 2
-                        for (int g = 0; g < (APE_EXP == 6 ? 0 : H / 4); ++g) {      // g = k-group * 2 + half: units 4g .. 4g+3 (APE_EXP 6: timing without it)
-                            const float4 x = __ldcg(cst + (size_t)g * ROWS);
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) {
-                                if (s + 4 * i < a.O) {
-                                    const float4 w = __ldg(reinterpret_cast<const float4*>(a.Wo + (size_t)(s + 4 * i) * H + 4 * g));
-                                    acc[i] = fmaf(w.x, x.x, acc[i]); acc[i] = fmaf(w.y, x.y, acc[i]);
-                                    acc[i] = fmaf(w.z, x.z, acc[i]); acc[i] = fmaf(w.w, x.w, acc[i]);
-                                }
-                            }
-                        }
+                        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(tc::pick4(v, i, s));
+                        tmem_ld_x32(tmem + t_lane + 128u + 32u, v);            // h_T x (W_o - fp16(W_o))^T
+                        tmem_ld_wait();
                         if (valid) {
                             const int e = row / a.n, smp = row - e * a.n;
                             const int b = e / a.nF, fb = stream_frame0(a.stream_frames, a.frame0, b), f = fb + e % a.nF;
 #pragma unroll
-                            for (int i = 0; i < 5; ++i) {
+                            for (int i = 0; i < 8; ++i) {      // this thread: outputs o = s, s+4, ... of its row (O <= 32)
                                 const int o = s + 4 * i;
-                                if (o < a.O && fb >= 0) {  // (an inactive stream keeps its prediction ring untouched)
+                                if (o < a.O && fb >= 0) {      // (an inactive stream keeps its prediction ring untouched)
+                                    const float yo = y[i] + __uint_as_float(tc::pick4(v, i, s)) + __ldg(a.bo + o);
                                     float* dst = a.preds + (((size_t)b * a.pred_ring + f % a.pred_ring) * a.n_out) * a.O + o;
-                                    if (a.n == 1 && a.n_out > 1) for (int s2 = 0; s2 < a.n_out; ++s2) dst[(size_t)s2 * a.O] = acc[i];
-                                    else dst[(size_t)smp * a.O] = acc[i];
+                                    if (a.n == 1 && a.n_out > 1) for (int s2 = 0; s2 < a.n_out; ++s2) dst[(size_t)s2 * a.O] = yo;
+                                    else dst[(size_t)smp * a.O] = yo;
                                 }
                             }
                         }
                     }
-                    epi_bar_sync();                            // the next tile's cell update rewrites the scratch
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&bars[C::BAR_OUT_DONE], rank);   // slot 1 may be refilled for the next tile
                 }
             }
         }
@@ -519,7 +529,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
             const uint32_t idesc = make_idesc_f16(256, 128);
             const uint64_t dX0 = make_desc(smem_u32(sAx), LBO_A, SBO), dW = make_desc(smem_u32(sW), LBO_B, SBO);
             const uint32_t bar_full = smem_u32(&bars[C::BAR_W_FULL]), bar_empty = smem_u32(&bars[C::BAR_W_EMPTY]);
-            uint32_t gl = 0, wslot = 0, gpiece = 0, gchunk = 0, hphase = 0;
+            uint32_t gl = 0, wslot = 0, gpiece = 0, gchunk = 0, hphase = 0, ph_outdone = 0;
+            // Output layer of the last layer (nn_models.py:189, last step only): h_T (TMEM) x [fp16(W_o) | W_o - fp16(W_o)]^T, one extra
+            // ring piece of KG/2 MMAs with N = 64 into the first 64 columns of accumulator slot 1.  It is issued by issuer 1 where
+            // that slot would be refilled for the next tile (or after the last tile); every role advances its ring position and
+            // piece number by one there.  slot_waited: chunk NCH-1's drain has been waited for.
+            const uint32_t idesc_out = make_idesc_f16(256, C::OUT_N);
+            auto out_piece = [&](bool slot_waited) {
+                if (my_slot == 1) {
+                    if (!slot_waited) mbar_wait_wd(&bars[C::BAR_SLOT_FREE + 1], (gchunk & 1) ^ 1);
+                    uint32_t spins = 0;
+                    while (!mbar_try_wait_addr(bar_full + (gpiece & (C::NFULL - 1)) * 8, (gpiece / C::NFULL) & 1)) { if (++spins > MBAR_WD_SPINS) __trap(); }
+                    mbar_wait_wd(&bars[C::BAR_H_READY + NCH - 1], hphase);             // all of h_T (slices are published in order)
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint64_t bd = make_desc(smem_u32(sW) + wslot * SLOT_BYTES, (C::OUT_N / 2) * 16, SBO);
+                        const uint32_t at = tmem + H_COL + (uint32_t)(T & 1) * H_COLS;   // step T-1 wrote h_T into buffer T & 1
+#pragma unroll
+                        for (uint32_t m = 0; m < KG / 2; ++m)
+                            mma_f16_ts<2>(tmem + 128, at + 8 * m, bd + m * (2 * (C::OUT_N / 2) * 16 >> 4), idesc_out, m > 0 ? 1u : 0u);
+                        commit_pair_addr(bar_empty + wslot * 8, 0x3);
+                        commit_pair(&bars[C::BAR_OUT_READY], 0x3);
+                    }
+                    __syncwarp();
+                    mbar_wait_wd(&bars[C::BAR_OUT_DONE], ph_outdone);                  // every epilogue warp has read its outputs
+                    ph_outdone ^= 1;
+                    fence_after_sync();
+                }
+                hphase ^= 1;                                   // the last step of a final layer publishes h_T: one more H_READY phase
+                wslot = wslot + 1 == NP ? 0 : wslot + 1;
+                ++gpiece;
+            };
+            bool out_pending = false;
             for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
                 for (int t = 0; t < T; ++t, ++gl) {
                     TCS_TR(long long* tr = (a.trace && blockIdx.x == 0 && tile == cluster_id && t == TRACE_T && lane == 0) ? a.trace : nullptr;)
@@ -536,6 +577,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     for (uint32_t i = 0; i < n_ent; ++i) {
                         const uint2 e_next = sched.e[which][i + 1 < n_ent ? i + 1 : i];   // fetched under this piece's waits
                         const uint32_t nmma = (e.x >> E_NMMA_SHIFT) & 0x1F;
+                        bool slot_waited = false;
+                        if ((e.x & E_OUT_BEFORE) && out_pending) {     // (first step of a tile) the previous tile's output layer
+                            if (my_slot == 1) {                // this entry's own slot wait, taken first: chunk NCH-1 has been drained
+                                mbar_wait_wd(&bars[C::BAR_SLOT_FREE + 1], (gchunk & 1) ^ 1);
+                                ++gchunk;
+                                slot_waited = true;
+                            }
+                            out_piece(true);
+                            out_pending = false;
+                        }
                         const uint32_t slot_b = wslot + 1 == NP ? 0 : wslot + 1;
                         if ((e.x & E_SLOT1) != my_slot) {      // the other issuer's piece: only the ring bookkeeping advances
                             wslot = nmma > SLOT_KG / 2 ? slot_b : wslot;
@@ -544,7 +595,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                             e = e_next;
                             continue;
                         }
-                        if (e.x & E_PRE_SLOT) {                // the epilogue has drained the chunk that used this slot before
+                        if ((e.x & E_PRE_SLOT) && !slot_waited) {   // the epilogue has drained the chunk that used this slot before
                             if (gchunk >= 1) mbar_wait_wd(&bars[C::BAR_SLOT_FREE + my_slot], (gchunk & 1) ^ 1);
                             ++gchunk;                          // (this issuer's count = uses of its slot so far)
                             TCS_TR(if (tr) tr[560 + ((2 * (gchunk - 1) + my_slot) & 7)] = clock64();)
@@ -605,26 +656,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     }
                     if (t > 0) hphase ^= 1;
                 }
+                out_pending = a.preds != nullptr;
             }
+            if (out_pending) out_piece(false);                 // the last tile's output layer
         } else if (warp == MMA_WARP && lane == 0) {
             // =============================== peer CTA: forward "piece landed in my ring" to the leader ==================
             uint32_t gpiece = 0;
-            for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters)
+            auto forward = [&]() {
+                mbar_wait_wd(&bars[C::BAR_W_FULL + (gpiece & (C::NFULL - 1))], (gpiece / C::NFULL) & 1);
+                mbar_arrive_remote(&bars[C::BAR_W_FULL + (gpiece & (C::NFULL - 1))], 0);
+                ++gpiece;
+            };
+            bool out_pending = false;
+            for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
                 for (int t = 0; t < T; ++t) {
-                    const uint32_t n_ent = sched.n[t == 0 ? 0 : 1];
+                    const int which = t == 0 ? 0 : 1;
+                    const uint32_t n_ent = sched.n[which];
 #pragma unroll 1
-                    for (uint32_t i = 0; i < n_ent; ++i, ++gpiece) {
-                        mbar_wait_wd(&bars[C::BAR_W_FULL + (gpiece & (C::NFULL - 1))], (gpiece / C::NFULL) & 1);
-                        mbar_arrive_remote(&bars[C::BAR_W_FULL + (gpiece & (C::NFULL - 1))], 0);
+                    for (uint32_t i = 0; i < n_ent; ++i) {
+                        if (out_pending && (sched.e[which][i].x & E_OUT_BEFORE)) { forward(); out_pending = false; }   // the W_o piece
+                        forward();
                     }
                 }
+                out_pending = a.preds != nullptr;
+            }
+            if (out_pending) forward();
         }
     } else if (lane == 0) {
         // =================================== weight-ring producer (one lane per CTA) =====================================
         const uint8_t* Wc = a.W + (size_t)rank * w_bytes;      // this CTA's half of the layer's weight tiles
         uint32_t wslot = 0, wphase = 0, gpiece = 0;
-        bool wrapped = false;
-        for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters)
+        bool wrapped = false, out_pending = false;
+        auto out_piece = [&]() {                               // this CTA's tile of the output-layer operand: one ring slot
+            uint64_t* full = &bars[C::BAR_W_FULL + (gpiece & (C::NFULL - 1))];
+            if (wrapped) mbar_wait_wd(&bars[C::BAR_W_EMPTY + wslot], wphase ^ 1);
+            mbar_arrive_expect_tx(full, C::OUT_BYTES);
+            bulk_g2s(sW + wslot * SLOT_BYTES, a.Wo16 + (size_t)rank * C::OUT_BYTES, C::OUT_BYTES, full);
+            if (++wslot == NP) { wslot = 0; wphase ^= 1; wrapped = true; }
+            ++gpiece;
+        };
+        for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
             for (int t = 0; t < T; ++t) {
                 TCS_TR(long long* tr = (a.trace && blockIdx.x == 0 && tile == cluster_id && t == TRACE_T) ? a.trace : nullptr;)
                 const int which = t == 0 ? 0 : 1;
@@ -632,6 +703,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 #pragma unroll 1
                 for (uint32_t i = 0; i < n_ent; ++i, ++gpiece) {
                     const uint32_t ex = sched.e[which][i].x;
+                    if (out_pending && (ex & E_OUT_BEFORE)) { out_piece(); out_pending = false; }
                     uint32_t kg_left = ((ex >> E_NMMA_SHIFT) & 0x1F) * 2, src_kg = ex >> E_SRC_SHIFT;
                     uint64_t* full = &bars[C::BAR_W_FULL + (gpiece & (C::NFULL - 1))];      // one "landed" barrier per piece
                     TCS_TR(if (tr && i < 48) tr[256 + 2 * i] = clock64();)
@@ -648,6 +720,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     TCS_TR(if (tr && i < 48) tr[257 + 2 * i] = clock64();)
                 }
             }
+            out_pending = a.preds != nullptr;
+        }
+        if (out_pending) out_piece();
     }
     __syncwarp();
     fence_before_sync();
@@ -664,6 +739,7 @@ int launch_layer(int H, const TcLayerArgs& a, int sm_count, cudaStream_t st) {
     if (H != 256) return APE_ERR_UNSUPPORTED;
     using C = Cfg<256>;
     if (a.kgx < 2 || a.kgx > C::KG || (a.kgx & 1) || !a.cstate) return APE_ERR_UNSUPPORTED;
+    if (a.preds && (!a.Wo16 || a.O > (int)C::OUT_N / 2)) return APE_ERR_UNSUPPORTED;
     Schedule sched{};
     for (int which = 0; which < 2; ++which) {
         Recorder r{sched.e[which], 0, a.kgx, C::KG, 0u, false};

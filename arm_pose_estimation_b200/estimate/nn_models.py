@@ -59,7 +59,7 @@ def pack_lstm_weights_tc(state):
     K-major no-swizzle tiles ``[k-group][64][8]`` halfs - first the input weights (layer 0: K zero-padded to a
     multiple of 16), then the recurrent weights; after both CTAs the bias ``b_ih + b_hh`` in column order 4u + g,
     scaled for the epilogue's ``sigmoid(x) = 0.5 + 0.5 tanh(x / 2)`` form: 0.5 b for i, f, o and b for g, so every
-    tanh argument comes out of one FMA.  After all layers: ``output_layer.weight`` (first 16 rows) as two fp16 operand tiles, rounding and remainder."""
+    tanh argument comes out of one FMA.  After all layers: ``output_layer.weight`` (first 16 rows; 32 for H = 256) as two fp16 operand tiles, rounding and remainder."""
     st = {k: np.asarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
           for k, v in state.items()}
     I, H, L, O = lstm_dims(st)
@@ -85,12 +85,14 @@ def pack_lstm_weights_tc(state):
     # output layer as a tensor-core operand (the H <= 128 kernel multiplies h_T by it, N = 32): CTA 0 holds the fp16 rounding of
     # W_o for the 16 outputs (zero rows beyond O), CTA 1 the fp16 remainder W_o - fp16(W_o) - the kernel sums the two products, so
     # W_o enters with ~22 bits; each as a K-major tile [H/8][16][8] halfs
-    w_full = np.zeros((16, H), np.float32)
-    w_full[: min(O, 16)] = st["output_layer.weight"][:16]
+    # (the H = 256 kernel does the same with 32 output columns per CTA)
+    n_cols = 32 if H > 128 else 16
+    w_full = np.zeros((n_cols, H), np.float32)
+    w_full[: min(O, n_cols)] = st["output_layer.weight"][:n_cols]
     w_hi = w_full.astype(np.float16)
     w_lo = (w_full - w_hi.astype(np.float32)).astype(np.float16)
     for w in (w_hi, w_lo):
-        parts.append(np.ascontiguousarray(w.reshape(16, H // 8, 8).transpose(1, 0, 2)).view(np.uint8).ravel())
+        parts.append(np.ascontiguousarray(w.reshape(n_cols, H // 8, 8).transpose(1, 0, 2)).view(np.uint8).ravel())
     return np.ascontiguousarray(np.concatenate(parts))
 
 

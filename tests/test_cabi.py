@@ -126,6 +126,15 @@ def test_tcs_schedule_covers_every_operand_once(kgx):
             assert sorted(cover_x[c]) == list(range(kgx))
             assert sorted(cover_h[c]) == ([] if first_step else list(range(32)))
         assert begun == list(range(NCH)) and sorted(done) == list(range(NCH)) and x_done == [NCH - 2, NCH - 1]
+        # the previous tile's output-layer product goes where accumulator slot 1 is first refilled: before chunk 1's first piece of
+        # a tile's first step, and nowhere else
+        out_before = [i for i, (x, _) in enumerate(ent) if x & 64]
+        if first_step:
+            assert len(out_before) == 1
+            x = ent[out_before[0]][0]
+            assert (x >> 17) // (kgx + 32) == 1 and x & 8 and x & 4 and not x & 2
+        else:
+            assert out_before == []
         if not first_step:                                              # only ONE small piece may follow the last K-slice of h_t
             last_slice = [i for i, (x, _) in enumerate(ent) if (x >> 13) & 0xF == NCH]
             assert ((ent[last_slice[0]][0] >> 8) & 0x1F) == SLICE_KG // 2 and ent[last_slice[0]][0] & 16
