@@ -300,12 +300,12 @@ def run_ours(args, rank, world, local_rank):
                     "peak_source": f"148 SM x 128 FFMA/clk x 2 x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz (nominal fp32 FMA peak at max SM clock; "
                                    f"MEASURED_PEAKS.json [{peak_src}] has no fp32 figure)",
                     "frac_of_bf16_tensor_peak": achieved / peaks["bf16_tflops"]}
-    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r1_final_ncu_summary.md:
+    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r1g_ncu_summary.md:
     # dram__bytes_read.sum + dram__bytes_write.sum of launch 1); null for configurations that were not captured
-    traffic = {("tc", 128, 1024, 100): 2.005248e6 + 102.449152e6, ("tc", 256, 1024, 100): 5.361920e6 + 512.0}.get(
+    traffic = {("tc", 128, 1024, 100): 2.006784e6 + 106.458880e6, ("tc", 256, 1024, 100): 5.356288e6 + 6656.0}.get(
         (be.lstm_variant, H, count, n)) if args.workload in ("uarm_1024x100", "watch_only_1024x100") else None
     roofline.update({"flops_per_launch": dom_flops, "ms_per_launch": dom_ms, "layer_ms": [float(v) for v in acc], "traffic": traffic,
-                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_final_ncu_summary.md)"})
+                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1g_ncu_summary.md)"})
 
     line = {
         "metric": METRIC, "value": total_est / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -411,12 +411,12 @@ def realtime_latency(BatchedEstimator, N, syn, frames=300):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="uarm_1024x100", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-frames", type=int, default=400, help="frames per worker of the bounded cpu_baseline sample")
-    ap.add_argument("--ref-frames", type=int, default=100, help="--impl reference: frames per worker per step")
+    ap.add_argument("--ref-frames", type=int, default=50, help="--impl reference: frames per worker per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-realtime", action="store_true", help="skip the configs[1] single-stream latency leg")
     ap.add_argument("--no-other-models", action="store_true", help="skip the throughput legs of the two H = 256 models")
