@@ -24,7 +24,7 @@ KSLICE = 16                      # csrc/ape_lstm_pack.h: APE_KSLICE
 SYMBOLS = (
     "ape_abi_version", "ape_last_cuda_error", "ape_device_info", "ape_lstm_blob_floats", "ape_features",
     "ape_mc_lstm_workspace_bytes", "ape_mc_lstm_fma", "ape_mc_lstm_tc_supported", "ape_lstm_tc_blob_bytes",
-    "ape_mc_lstm_tc_workspace_bytes", "ape_mc_lstm_tc", "ape_philox_masks", "ape_ff_blob_floats", "ape_mc_ff", "ape_fk_reduce", "ape_msg_from_est",
+    "ape_mc_lstm_tc_workspace_bytes", "ape_mc_lstm_tc", "ape_philox_masks", "ape_ff_blob_floats", "ape_mc_ff", "ape_dense_act", "ape_fk_reduce", "ape_msg_from_est",
     "ape_selfcheck_philox", "ape_selfcheck_keep8", "ape_selfcheck_features", "ape_selfcheck_row_pose", "ape_selfcheck_tcs_schedule",
     "ape_selftest_umma",
 )
@@ -102,6 +102,8 @@ def load():
     lib.ape_philox_masks.argtypes = [u64, u32, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp]
     lib.ape_ff_blob_floats.restype = i32
     lib.ape_ff_blob_floats.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_int64)]
+    lib.ape_dense_act.restype = i32
+    lib.ape_dense_act.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.ape_mc_ff.restype = i32
     lib.ape_mc_ff.argtypes = [vp, i32, i32, i32, i32, f32, vp, i32, i32, i32, vp, u64, u32, u32, vp, vp]
     lib.ape_fk_reduce.restype = i32

@@ -81,7 +81,55 @@ __global__ void __launch_bounds__(FF_THREADS) mc_ff_kernel(FfArgs a) {
     }
 }
 
+// One dense layer  y = act(x W^T + b)  over many rows: the input layer of ImuPoseLSTM (nn_models.py:210-249: Linear(I, 256) + relu in
+// front of a plain 2-layer LSTM).  W^T [K][H] pre-transposed like the feed-forward blob; a CTA stages DENSE_ROWS input rows in
+// shared memory and its threads sweep the output units (coalesced weight reads, DENSE_ROWS accumulators per thread).
+constexpr int DENSE_ROWS = 8;
+
+__global__ void __launch_bounds__(FF_THREADS) dense_act_kernel(const float* __restrict__ wt, const float* __restrict__ bias,
+                                                               const float* __restrict__ x, float* __restrict__ y,
+                                                               int rows, int K, int H, int act) {
+    extern __shared__ float sx[];                      // [DENSE_ROWS][K]
+    const int row0 = blockIdx.x * DENSE_ROWS, tid = threadIdx.x;
+    const int nr = min(DENSE_ROWS, rows - row0);
+    for (int i = tid; i < DENSE_ROWS * K; i += FF_THREADS) sx[i] = i < nr * K ? x[(size_t)row0 * K + i] : 0.0f;
+    __syncthreads();
+    for (int j = tid; j < H; j += FF_THREADS) {
+        float acc[DENSE_ROWS];
+        const float b = bias[j];
+#pragma unroll
+        for (int r = 0; r < DENSE_ROWS; ++r) acc[r] = b;
+        for (int k = 0; k < K; ++k) {
+            const float w = __ldg(wt + (size_t)k * H + j);
+#pragma unroll
+            for (int r = 0; r < DENSE_ROWS; ++r) acc[r] = fmaf(w, sx[r * K + k], acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < DENSE_ROWS; ++r) {
+            if (r < nr) {
+                float v = acc[r];
+                if (act == 1) v = v > 0.0f ? v : 0.0f;               // relu
+                else if (act == 2) v = v > 0.0f ? v : 0.01f * v;     // leaky_relu(0.01)
+                y[(size_t)(row0 + r) * H + j] = v;
+            }
+        }
+    }
+}
+
 }  // namespace ape
+
+extern "C" int ape_dense_act(const float* wt, const float* bias, const float* x, float* y, int rows, int K, int H, int act,
+                             void* stream) {
+    using namespace ape;
+    if (!wt || !bias || !x || !y || rows < 0 || K < 1 || H < 1 || act < 0 || act > 2) return APE_ERR_BAD_ARG;
+    if (rows == 0) return APE_OK;
+    const size_t smem = sizeof(float) * (size_t)DENSE_ROWS * K;
+    if (smem > 200 * 1024) return APE_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024)
+        APE_CUDA_TRY(cudaFuncSetAttribute(dense_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dense_act_kernel<<<(rows + DENSE_ROWS - 1) / DENSE_ROWS, FF_THREADS, smem, (cudaStream_t)stream>>>(wt, bias, x, y, rows, K, H, act);
+    return check_launch();
+}
 
 extern "C" int ape_ff_blob_floats(int I, int H, int Lh, int O, int64_t* floats) {
     if (!floats || I < 1 || H < 1 || Lh < 0 || O < 1) return APE_ERR_BAD_ARG;

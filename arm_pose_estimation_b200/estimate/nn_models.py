@@ -377,6 +377,67 @@ class DropoutFF2D(DropoutFF):
         return out.reshape(n_samples, self.output_size)
 
 
+class ImuPoseLSTM:
+    """``Linear(input, 256) + relu -> LSTM(256, 256, 2 layers) -> Linear(256, output)`` behind the reference API
+    (``nn_models.py:210-249``; hidden size and depth are fixed there, the constructor keeps the unused arguments).  The input
+    layer is one dense kernel (``ape_dense_act``), the rest the fp32 MC-LSTM kernel on the 256 activations.  Inter-layer
+    dropout is only active in train mode; ``monte_carlo_predictions`` is a plain forward pass, like the reference's."""
+
+    WIDTH, DEPTH = 256, 2
+
+    def __init__(self, input_size, hidden_layer_size=None, hidden_layer_count=None, output_size=None, dropout=0.2, philox_seed=None):
+        self.input_size, self.output_size = int(input_size), int(output_size)
+        self._core = DropoutLSTM(self.WIDTH, self.WIDTH, self.DEPTH, self.output_size, dropout, philox_seed)
+        self.lstm = self._core.lstm
+        self._state = None
+        self._w_in = None                    # (W^T [I][256], b [256]) on the device, built lazily
+
+    def load_state_dict(self, state):
+        w = state["input_layer.weight"]
+        if tuple(w.shape) != (self.WIDTH, self.input_size):
+            raise RuntimeError(f"input_layer.weight is {tuple(w.shape)}, model expects {(self.WIDTH, self.input_size)}")
+        self._state = {k: torch.as_tensor(np.asarray(v.detach().cpu() if isinstance(v, torch.Tensor) else v, dtype=np.float32))
+                       for k, v in state.items()}
+        self._core.load_state_dict({k: v for k, v in self._state.items() if not k.startswith("input_layer.")})
+        self._w_in = None
+        return self
+
+    def state_dict(self):
+        return dict(self._state)
+
+    def eval(self):
+        self.lstm.eval()
+        return self
+
+    def train(self, mode=True):
+        self.lstm.train(mode)
+        return self
+
+    def forward(self, x, hs=None):
+        """``x [batch, sequence, input] -> [batch, sequence, output]`` (nn_models.py:237-245)."""
+        _require_cuda()
+        if self._state is None:
+            raise UserWarning("model has no weights: call load_state_dict first")
+        if x.dim() != 3 or x.shape[2] != self.input_size:
+            raise UserWarning(f"expected x of shape [batch, sequence, {self.input_size}], got {tuple(x.shape)}")
+        if self._w_in is None:
+            self._w_in = (self._state["input_layer.weight"].t().contiguous().cuda(), self._state["input_layer.bias"].contiguous().cuda())
+        host_in = not x.is_cuda
+        xd = x.detach().to(device="cuda", dtype=torch.float32).contiguous()
+        E, T, _ = xd.shape
+        act = torch.empty((E, T, self.WIDTH), dtype=torch.float32, device="cuda")
+        N.check(N.load().ape_dense_act(N.ptr(self._w_in[0]), N.ptr(self._w_in[1]), N.ptr(xd), N.ptr(act), E * T, self.input_size,
+                                       self.WIDTH, 1, N.current_stream_ptr()), "ape_dense_act")
+        out = self._core.forward(act, hs)
+        return out.cpu() if host_in else out
+
+    __call__ = forward
+
+    def monte_carlo_predictions(self, n_samples, x):
+        """The reference's model has no MC dropout path: a regular forward pass (nn_models.py:247-252)."""
+        return self(x, None)
+
+
 def load_deployed_model_from_hash(hash_str: str):
     """``(model, params)`` from ``<deploy>/nn/<hash>/{results.json, checkpoint.pt}`` (nn_models.py:373-415);
     the checkpoint is the ``(model_state, optimizer_state)`` tuple the reference saves."""
@@ -392,6 +453,8 @@ def load_deployed_model_from_hash(hash_str: str):
         params["model"] = DropoutLSTM
     elif params["model"] == "DropoutFF":
         params["model"] = DropoutFF
+    elif params["model"] == "ImuPoseLSTM":
+        params["model"] = ImuPoseLSTM
     else:
         raise UserWarning(f"{params['model']} not handled")
     nn_model = params["model"](

@@ -69,6 +69,17 @@ def synth_state_dict(I, H, L, O, seed=1234):
     return sd
 
 
+def synth_imu_pose_state_dict(I, O, seed=1234):
+    """State dict of the reference's ``ImuPoseLSTM`` (``input_layer.*`` + a 2-layer LSTM(256, 256) + ``output_layer.*``,
+    nn_models.py:223-234) with seeded numpy values like ``synth_state_dict``."""
+    rng = np.random.default_rng(seed)
+    k = 1.0 / np.sqrt(I)
+    sd = {"input_layer.weight": rng.uniform(-k, k, size=(256, I)).astype(np.float32),
+          "input_layer.bias": rng.uniform(-k, k, size=(256,)).astype(np.float32)}
+    sd.update(synth_state_dict(256, 256, 2, O, seed + 1))
+    return sd
+
+
 def write_synthetic_deploy(dst, seed=1234):
     """Create a deploy directory ``dst`` (results.json + stats of this package, plus a seeded synthetic
     ``checkpoint.pt`` per deployed hash, saved as the ``(model_state, optimizer_state)`` tuple the reference's

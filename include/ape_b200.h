@@ -160,6 +160,13 @@ int ape_mc_ff(const float* blob, int I, int H, int Lh, int O, float dropout_p, c
               int n_samples, int mask_mode, const uint8_t* masks, uint64_t philox_seed, uint32_t stream_id0,
               uint32_t frame0, float* preds, void* stream);
 
+/*
+ * One dense layer over many rows, y = act(x W^T + b): the input layer of ImuPoseLSTM (nn_models.py:210-249: Linear + relu in front
+ * of a plain LSTM; the LSTM itself runs through ape_mc_lstm_fma with x_dense).
+ *   wt [K][H] float32 (the layer's weight transposed), bias [H], x [rows][K], y [rows][H]; act 0 none, 1 relu, 2 leaky_relu(0.01)
+ */
+int ape_dense_act(const float* wt, const float* bias, const float* x, float* y, int rows, int K, int H, int act, void* stream);
+
 /* ---- stage 3: targets -> quaternions + forward kinematics + MC reduction ----------------------- */
 /*
  * Replaces the de-normalisation of estimator.py:108-109, the smoothing stack of :112-118,

@@ -298,12 +298,30 @@ def golden_ff():
     np.savez_compressed(HERE / "ff.npz", **out)
 
 
+def golden_imu_pose_lstm():
+    print("ImuPoseLSTM: Linear + relu -> LSTM(256, 256, 2) -> Linear, eval mode")
+    from oracle import imu_pose_lstm as OI
+    model = ref_nn.ImuPoseLSTM(input_size=20, hidden_layer_size=0, hidden_layer_count=0, output_size=12).eval()
+    state = syn.synth_imu_pose_state_dict(20, 12, 99)           # (1 M weights: the fixture carries the seed, not the values)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()})
+    x = np.random.default_rng(6).normal(size=(5, 7, 20)).astype(np.float32)
+    with torch.no_grad():
+        y = model(torch.from_numpy(x)).numpy()
+        y_mc = model.monte_carlo_predictions(n_samples=9, x=torch.from_numpy(x[:1])).numpy()
+    close(OI.forward(state, x), y, 2e-6, "ImuPoseLSTM eval")
+    close(y_mc, y[:1], 1e-6, "ImuPoseLSTM monte_carlo_predictions == forward (up to batch-size dependent rounding)")
+    np.savez_compressed(HERE / "imu_pose_lstm.npz", x=x, y=y, y_mc=y_mc, weight_seed=99)
+
+
 def main():
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     with tempfile.TemporaryDirectory() as tmp:
         make_ref_deploy(tmp)
         if only == "ff":
             golden_ff()
+            return
+        if only == "imu_pose_lstm":
+            golden_imu_pose_lstm()
             return
         golden_tables()
         golden_quat()
@@ -312,6 +330,7 @@ def main():
         golden_lstm()
         golden_e2e()
         golden_ff()
+        golden_imu_pose_lstm()
     print("fixtures written to", HERE)
 
 
