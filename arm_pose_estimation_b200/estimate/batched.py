@@ -99,7 +99,8 @@ class PendingEstimate:
 
 
 class BatchedEstimator:
-    N_SLOTS = 4      # staging / result buffer sets: up to N_SLOTS - 1 submitted calls may be outstanding while the next is staged
+    N_SLOTS = 6      # staging / result buffer sets: up to N_SLOTS - 1 submitted calls may be outstanding while the next is staged
+                     # (measured end to end, uarm 1024 x 100: 3 outstanding 0.413 ms/step, 5 outstanding 0.392, 7 outstanding 0.391)
 
     def __init__(self, kind, layout, state, seq_len, y_targets, stats, n_streams, mc_samples,
                  smooth=1, dropout=0.2, bonemap=None, frames_per_call=1, emit_samples=True, normalize=True,
