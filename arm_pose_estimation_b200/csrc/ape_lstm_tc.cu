@@ -516,7 +516,9 @@ template <int H> static int launch(const TcLayerArgs& a, int sm_count, cudaStrea
 
 // rows per CTA of layer 0 (one row per estimate): a small batch is spread over more CTA pairs, 32 rows each
 constexpr int TC_MAX_SMS = 160;                    // cell-state scratch is sized for this many CTAs (B200: 148)
-static int tc_rpc0(long long E) { return E >= 16384 ? 128 : 32; }
+// (128 rows from 512 estimates on: a 32-row CTA takes as long per step as a full one - its 4 live epilogue warps share one SM quarter -
+// so spreading layer 0 of a large batch over 4x the SMs only takes them away from the big layers that run beside it: +1 % per step)
+static int tc_rpc0(long long E) { return E >= 512 ? 128 : 32; }
 static int tc_kgx(int layer, int I, int H) { return layer == 0 ? ape_pack_kin_pad(0, I, H) / 8 : H / 8; }
 static size_t tc_layer_bytes(int layer, int I, int H) {
     return (size_t)2 * (H / 32) * (tc_kgx(layer, I, H) + H / 8) * 64 * 16 + (size_t)4 * H * 4;
