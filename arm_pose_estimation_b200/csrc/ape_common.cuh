@@ -43,9 +43,15 @@ template <typename F> APE_HD Quat<F> qconj(const Quat<F>& q) { return {q.w, -q.x
 
 // q (x) [0,v] (x) conj(q) without normalising q (transformations.py:105-121)
 template <typename F> APE_HD Vec3<F> qrot(const Quat<F>& q, const Vec3<F>& v) {
-    Quat<F> p = {F(0), v.x, v.y, v.z};
-    Quat<F> r = qmul(qmul(q, p), qconj(q));
-    return {r.x, r.y, r.z};
+    // the two Hamilton products written out without the terms that multiply the zero scalar part of [0, v] and without the
+    // scalar part of the result (which is not used): the same sums in the same order
+    const Quat<F> a = {-q.x * v.x - q.y * v.y - q.z * v.z,
+                       q.w * v.x + q.y * v.z - q.z * v.y,
+                       q.w * v.y - q.x * v.z + q.z * v.x,
+                       q.w * v.z + q.x * v.y - q.y * v.x};
+    return {-a.w * q.x + a.x * q.w - a.y * q.z + a.z * q.y,
+            -a.w * q.y + a.x * q.z + a.y * q.w - a.z * q.x,
+            -a.w * q.z - a.x * q.y + a.y * q.x + a.z * q.w};
 }
 // conjugate / squared norm (transformations.py:244-254)
 template <typename F> APE_HD Quat<F> qinv(const Quat<F>& q) {

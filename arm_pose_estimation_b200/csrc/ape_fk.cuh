@@ -5,6 +5,17 @@
 
 namespace ape {
 
+// 1 / sqrt(x): every normalisation below multiplies by it (one MUFU.RSQ, <= 2 ulp, on the device instead of an IEEE square root
+// plus three IEEE divisions - those were two thirds of the stage-3 kernel's instructions)
+APE_HD double inv_sqrt(double x) { return 1.0 / sqrt(x); }
+APE_HD float inv_sqrt(float x) {
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
 // Gram-Schmidt of a1 = (c0,c2,c4), a2 = (c1,c3,c5) (transformations.py:616-626), then rotation matrix ->
 // quaternion.  The reference takes the dominant eigenvector of transforms3d's 4x4 K matrix (:521-545);
 // for the orthonormal matrix produced here that equals the closed-form conversion, evaluated with the
@@ -12,33 +23,34 @@ namespace ape {
 // `bad` is set when a column norm is zero / non-finite (the reference raises LinAlgError there).
 template <typename F> APE_HD Quat<F> six_to_quat(const F* c, bool& bad) {
     const F a1x = c[0], a1y = c[2], a1z = c[4], a2x = c[1], a2y = c[3], a2z = c[5];
-    const F n1 = sqrt(a1x * a1x + a1y * a1y + a1z * a1z);
-    const F b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
+    const F s1 = a1x * a1x + a1y * a1y + a1z * a1z, i1 = inv_sqrt(s1);
+    const F b1x = a1x * i1, b1y = a1y * i1, b1z = a1z * i1;
     const F d = b1x * a2x + b1y * a2y + b1z * a2z;
     const F ux = a2x - d * b1x, uy = a2y - d * b1y, uz = a2z - d * b1z;
-    const F n2 = sqrt(ux * ux + uy * uy + uz * uz);
-    const F b2x = ux / n2, b2y = uy / n2, b2z = uz / n2;
+    const F s2 = ux * ux + uy * uy + uz * uz, i2 = inv_sqrt(s2);
+    const F b2x = ux * i2, b2y = uy * i2, b2z = uz * i2;
     const F b3x = b1y * b2z - b1z * b2y, b3y = b1z * b2x - b1x * b2z, b3z = b1x * b2y - b1y * b2x;
-    if (!(n1 > F(0)) || !(n2 > F(0)) || !(n1 < F(1e30)) || !(n2 < F(1e30))) bad = true;
+    // a zero / non-finite / absurdly long column (squared norms: the bound is 1e30 squared, infinity in float)
+    if (!(s1 > F(0)) || !(s2 > F(0)) || !(s1 < F(1e30) * F(1e30)) || !(s2 < F(1e30) * F(1e30))) bad = true;
     // R = [b1 b2 b3] as columns: r_ij = row i, column j
     const F r00 = b1x, r01 = b2x, r02 = b3x, r10 = b1y, r11 = b2y, r12 = b3y, r20 = b1z, r21 = b2z, r22 = b3z;
     const F fw = F(1) + r00 + r11 + r22, fx = F(1) + r00 - r11 - r22;
     const F fy = F(1) - r00 + r11 - r22, fz = F(1) - r00 - r11 + r22;
     Quat<F> q;
     if (fw >= fx && fw >= fy && fw >= fz) {
-        const F s = F(0.5) / sqrt(fw);
+        const F s = F(0.5) * inv_sqrt(fw);
         q = {fw * s, (r21 - r12) * s, (r02 - r20) * s, (r10 - r01) * s};
     } else if (fx >= fy && fx >= fz) {
-        const F s = F(0.5) / sqrt(fx);
+        const F s = F(0.5) * inv_sqrt(fx);
         q = {(r21 - r12) * s, fx * s, (r01 + r10) * s, (r02 + r20) * s};
     } else if (fy >= fz) {
-        const F s = F(0.5) / sqrt(fy);
+        const F s = F(0.5) * inv_sqrt(fy);
         q = {(r02 - r20) * s, (r01 + r10) * s, fy * s, (r12 + r21) * s};
     } else {
-        const F s = F(0.5) / sqrt(fz);
+        const F s = F(0.5) * inv_sqrt(fz);
         q = {(r10 - r01) * s, (r02 + r20) * s, (r12 + r21) * s, fz * s};
     }
-    const F inv = F(1) / sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);   // eigh returns a unit vector
+    const F inv = inv_sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);   // eigh returns a unit vector
     const F sg = q.w < F(0) ? -inv : inv;
     return {q.w * sg, q.x * sg, q.y * sg, q.z * sg};
 }

@@ -330,6 +330,8 @@ def run_ours(args, rank, world, local_rank):
                                 for w in ("watch_only_1024x100", "pocket_1024x100")}
     if rank == 0 and world == 1 and not args.no_realtime:
         line["realtime"] = realtime_latency(BatchedEstimator, N, syn)
+    if rank == 0 and world == 1 and not args.no_other_models:
+        line["fk_roofline"] = fk_standalone(N, syn, torch, kind, n, measured_peaks()[0])
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         workers = max(1, min(os.cpu_count() or 1, 64))
         ref = CpuReference(kind, n, smooth, workers)
@@ -343,6 +345,42 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def fk_standalone(N, syn, torch, kind, n, peaks, E=32768, reps=20):
+    """Stage 3 on its own (judged separately against the HBM roofline): `ape_fk_reduce` over E estimates x n MC rows
+    of random network targets - 157 MB of predictions in, messages + std + per-sample positions out, far beyond the 126 MB L2.
+    Algorithmic bytes per estimate: 4 S O in + 100 (message) + 24 (std) + 24 S (sample positions)."""
+    spec = syn.kind_spec(kind)
+    O, tgt = spec["O"], {12: N.TARGET_ORI_CAL_LARM_UARM, 14: N.TARGET_ORI_CAL_LARM_UARM_HIPS}[spec["O"]]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    preds = torch.randn((E, 1, n, O), generator=g, device="cuda", dtype=torch.float32)
+    yy_m = torch.as_tensor(np.asarray(spec["stats"]["yy_m"], np.float32)).cuda()
+    yy_s = torch.as_tensor(np.asarray(spec["stats"]["yy_s"], np.float32)).cuda()
+    from arm_pose_estimation_b200.data_types.bone_map import body_measurements_row
+    body = torch.as_tensor(body_measurements_row(None).astype(np.float32).ravel()).cuda()
+    msg = torch.empty((E, 25), device="cuda"); std = torch.empty((E, 6), device="cuda")
+    samples = torch.empty((E, n, 6), device="cuda"); status = torch.zeros(E, dtype=torch.int32, device="cuda")
+    lib, st = N.load(), N.current_stream_ptr()
+
+    def run():
+        N.check(lib.ape_fk_reduce(N.ptr(preds), 1, N.ptr(yy_m), N.ptr(yy_s), N.ptr(body), tgt, O, E, 1, 0, None, n, 1,
+                                  N.ptr(msg), N.ptr(samples), N.ptr(std), None, N.ptr(status), st), "ape_fk_reduce")
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    bytes_per_est = 4 * n * O + 100 + 24 + 24 * n
+    gbs = E * bytes_per_est / (ms * 1e-3) / 1e9
+    return {"kernel": "fk_reduce_kernel (stage 3 standalone)", "estimates": E, "mc_rows": n, "ms_per_launch": ms,
+            "bytes_per_estimate": bytes_per_est, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": gbs / peaks["hbm_gbs"], "estimates_per_s": E / (ms * 1e-3),
+            "l2": f"{E * bytes_per_est / 1e6:.0f} MB per launch: larger than the 126 MB L2"}
 
 
 def quick_throughput(workload, lstm, BatchedEstimator, N, syn, torch, steps=30, warmup=5):
