@@ -53,6 +53,11 @@ template <typename F> APE_HD Vec3<F> qrot(const Quat<F>& q, const Vec3<F>& v) {
             -a.w * q.y + a.x * q.z + a.y * q.w - a.z * q.x,
             -a.w * q.z - a.x * q.y + a.y * q.x + a.z * q.w};
 }
+// qrot for a vector along the x axis, v = (vx, 0, 0) - the default bone vectors (bone_map.py:42-45) - written out: vx times the
+// first column of the (unnormalised) rotation matrix of q.  10 operations instead of 42.
+template <typename F> APE_HD Vec3<F> qrot_x(const Quat<F>& q, F vx) {
+    return {vx * (q.w * q.w + q.x * q.x - q.y * q.y - q.z * q.z), vx * F(2) * (q.x * q.y + q.w * q.z), vx * F(2) * (q.x * q.z - q.w * q.y)};
+}
 // conjugate / squared norm (transformations.py:244-254)
 template <typename F> APE_HD Quat<F> qinv(const Quat<F>& q) {
     F n = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;

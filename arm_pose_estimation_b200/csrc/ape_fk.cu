@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
     body.larm_vec = {a.body9[0], a.body9[1], a.body9[2]};
     body.uarm_vec = {a.body9[3], a.body9[4], a.body9[5]};
     body.uarm_orig = {a.body9[6], a.body9[7], a.body9[8]};
+    body.bones_along_x = bones_are_along_x(body);      // (the default skeleton: a uniform branch)
 
     Quat<float> q0l{}, q0u{}, q0h{}, sl{0, 0, 0, 0}, su{0, 0, 0, 0}, sh{0, 0, 0, 0};
     float piv[6] = {0, 0, 0, 0, 0, 0}, d1[6] = {0, 0, 0, 0, 0, 0}, d2[6] = {0, 0, 0, 0, 0, 0};

@@ -61,7 +61,13 @@ template <typename F> APE_HD Quat<F> hips_quat(F s, F c) {
     return {cos(y * F(0.5)), F(0), sin(y * F(0.5)), F(0)};
 }
 
-template <typename F> struct Body { Vec3<F> larm_vec, uarm_vec, uarm_orig; };
+template <typename F> struct Body {
+    Vec3<F> larm_vec, uarm_vec, uarm_orig;
+    bool bones_along_x = false;      // both bone vectors are (len, 0, 0): chain() may take the short rotation (set by the caller)
+};
+template <typename F> APE_HD bool bones_are_along_x(const Body<F>& b) {
+    return b.larm_vec.y == F(0) && b.larm_vec.z == F(0) && b.uarm_vec.y == F(0) && b.uarm_vec.z == F(0);
+}
 
 template <typename F> struct RowPose {
     Quat<F> larm, uarm, hips;
@@ -73,8 +79,13 @@ template <typename F> APE_HD Vec3<F> vadd(const Vec3<F>& a, const Vec3<F>& b) { 
 // shoulder -> elbow -> hand from the three quaternions (estimate_joints.py:61-63 / :84-85, compose_msg.py:59-61 / :92-93)
 template <typename F> APE_HD void chain(int target, const Body<F>& body, RowPose<F>& r) {
     r.shoulder = target == APE_TARGET_ORI_CAL_LARM_UARM ? body.uarm_orig : qrot(r.hips, body.uarm_orig);
-    r.elbow = vadd(qrot(r.uarm, body.uarm_vec), r.shoulder);
-    r.hand = vadd(qrot(r.larm, body.larm_vec), r.elbow);
+    if (body.bones_along_x) {
+        r.elbow = vadd(qrot_x(r.uarm, body.uarm_vec.x), r.shoulder);
+        r.hand = vadd(qrot_x(r.larm, body.larm_vec.x), r.elbow);
+    } else {
+        r.elbow = vadd(qrot(r.uarm, body.uarm_vec), r.shoulder);
+        r.hand = vadd(qrot(r.larm, body.larm_vec), r.elbow);
+    }
 }
 
 // One de-normalised target row -> quaternions + joint origins (estimate_joints.py:20-92).

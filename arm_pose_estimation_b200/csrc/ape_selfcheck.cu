@@ -41,6 +41,7 @@ template <typename F> static int row_pose_host(int target, const double* preds, 
     F p[20];
     for (int i = 0; i < O; ++i) p[i] = (F)preds[i];
     Body<F> body{{(F)body9[0], (F)body9[1], (F)body9[2]}, {(F)body9[3], (F)body9[4], (F)body9[5]}, {(F)body9[6], (F)body9[7], (F)body9[8]}};
+    body.bones_along_x = bones_are_along_x(body);       // the same path the kernel takes for this skeleton
     bool b = false;
     const RowPose<F> r = row_pose<F>(target, p, body, b);
     int k = 0;
