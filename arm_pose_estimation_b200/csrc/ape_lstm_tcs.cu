@@ -268,6 +268,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     cbuf[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     cbuf[1] = cbuf[0];
                     if (t > 0 && APE_EXP != 8) cbuf[0] = __ldcg(cst + (size_t)((4 * 0 + s) * 2 + 0) * ROWS);
+                    // The bias of half-pass hp+1 is requested at the end of half-pass hp's arithmetic, where few registers are live:
+                    // its ~40 cycles of L1 latency used to sit in front of the first FMA of every half-pass (ncu: a fifth of the
+                    // kernel's stall samples).
+                    float4 bnext[4];
+                    auto request_bias = [&](int hp1) {
+                        const float4* bias4 = reinterpret_cast<const float4*>(a.bias_s + ((hp1 >> 1) * 32 + 8 * s + 4 * (hp1 & 1)) * 4);
+                        bnext[0] = __ldg(bias4); bnext[1] = __ldg(bias4 + 1); bnext[2] = __ldg(bias4 + 2); bnext[3] = __ldg(bias4 + 3);
+                    };
+                    request_bias(0);
                     mbar_wait_wd(&bars[C::BAR_ACC_READY + 0], par0);
                     fence_after_sync();
                     tmem_ld_x16(tmem + t_lane + (uint32_t)(32 * s), rbuf[0]);
@@ -275,12 +284,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                     for (int hp = 0; hp < 2 * NCH; ++hp) {
                         const int c = hp >> 1, half = hp & 1;
                         const uint32_t* r = rbuf[hp & 1];
-                        // this half-pass's bias (warp-uniform addresses, L1-resident) is requested before anything waits
-                        const float4* bias4 = reinterpret_cast<const float4*>(a.bias_s + (c * 32 + 8 * s + 4 * half) * 4);
+                        // this half-pass's bias (warp-uniform addresses, L1-resident) was requested in the tail of the previous one
 #if APE_EXP == 10
                         const float4 bsv[4] = {make_float4(0.1f, 0.2f, 0.3f, 0.4f), make_float4(0.1f, 0.2f, 0.3f, 0.4f), make_float4(0.1f, 0.2f, 0.3f, 0.4f), make_float4(0.1f, 0.2f, 0.3f, 0.4f)};
 #else
-                        const float4 bsv[4] = {__ldg(bias4), __ldg(bias4 + 1), __ldg(bias4 + 2), __ldg(bias4 + 3)};
+                        const float4 bsv[4] = {bnext[0], bnext[1], bnext[2], bnext[3]};
 #endif
                         if (half == 0 && hp > 0 && !prefetched) {      // the chunk was not complete yet when the last half-pass looked
                             mbar_wait_wd(&bars[C::BAR_ACC_READY + (c & 1)], par0 ^ ((c >> 1) & 1));
@@ -364,6 +372,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
 #pragma unroll
                         for (int u = 0; u < 4; ++u) hv[u] = (1.0f - num[u]) * rcp_approx((1.0f + ev[4 * u + 3]) * (1.0f + num[u]));
 #endif
+                        if (hp + 1 < 2 * NCH && APE_EXP != 10) request_bias(hp + 1);
                         // cell state back to its scratch line (not needed after the last step)
                         if (t + 1 < T && APE_EXP != 8) __stcg(cst + (size_t)((4 * c + s) * 2 + half) * ROWS, make_float4(cn[0], cn[1], cn[2], cn[3]));
                         const int j = 4 * c + s;               // k-group of units 32c + 8s .. + 7
