@@ -300,12 +300,12 @@ def run_ours(args, rank, world, local_rank):
                     "peak_source": f"148 SM x 128 FFMA/clk x 2 x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz (nominal fp32 FMA peak at max SM clock; "
                                    f"MEASURED_PEAKS.json [{peak_src}] has no fp32 figure)",
                     "frac_of_bf16_tensor_peak": achieved / peaks["bf16_tflops"]}
-    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r1h_ncu_summary.md:
+    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r1i_ncu_summary.md:
     # dram__bytes_read.sum + dram__bytes_write.sum of launch 1); null for configurations that were not captured
-    traffic = {("tc", 128, 1024, 100): 1.932288e6 + 98.820352e6, ("tc", 256, 1024, 100): 5.387008e6 + 512.0}.get(
+    traffic = {("tc", 128, 1024, 100): 1.923840e6 + 98.600960e6, ("tc", 256, 1024, 100): 5.389056e6 + 46848.0}.get(
         (be.lstm_variant, H, count, n)) if args.workload in ("uarm_1024x100", "watch_only_1024x100") else None
     roofline.update({"flops_per_launch": dom_flops, "ms_per_launch": dom_ms, "layer_ms": [float(v) for v in acc], "traffic": traffic,
-                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1h_ncu_summary.md)"})
+                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1i_ncu_summary.md)"})
 
     line = {
         "metric": METRIC, "value": total_est / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
