@@ -252,7 +252,7 @@ class BatchedEstimator:
 
     # ---- device path -----------------------------------------------------------------------------------
     def step_device(self, raw, n_frames=None, masks=None, layer_ms=None, trace=None, trace_layer=1, raw_ready=False,
-                    _h2d_from=None, stream_frames=None, _frames_from=None, _out_slot=None, timeline=None):
+                    _h2d_from=None, stream_frames=None, _frames_from=None, _out_slot=None, timeline=None, _plain=False):
         """``raw``: device tensor ``[B, nF, ncols]`` float32 (nF <= frames_per_call).  Enqueues the three stages and returns an
         ``EstimateBatch`` of views into the estimator's device buffers (valid until the call after next).  ``raw_ready=True``
         promises that ``raw`` is already materialised (not pending on the current stream), which lets the pipelined path
@@ -307,7 +307,7 @@ class BatchedEstimator:
                                       N.ptr(self.msg), N.ptr(self.samples), N.ptr(self.std), None, N.ptr(self.status), stream_ptr),
                     "ape_fk_reduce")
 
-        if self.pipeline and layer_ms is None and trace is None:
+        if self.pipeline and layer_ms is None and trace is None and not _plain:
             # buffer set of this call: lane (stream + workspace) = call & 1; with lanes each workspace's two copies of layer 0's
             # output alternate as well, so stage 1 + layer 0 may run up to three calls ahead of the big kernels (whichever
             # launch's tail has room for their few dozen CTAs) and never gate the next call's first big layer
@@ -429,6 +429,70 @@ class BatchedEstimator:
             self.slot_event[slot] = ev
             self.copy_done[slot] = ev
         return PendingEstimate(self, slot, nF, out.frame0, ev)
+
+    # ---- single-call latency path: the whole call as one captured CUDA graph ------------------------------------
+    def step_graph(self, rows):
+        """``step`` for the latency-bound case (a few streams, one call at a time - BASELINE configs[1]): pinned H2D of the rows
+        and of the frame counter, the three stages and the pinned D2H are captured ONCE as a CUDA graph and replayed with one
+        launch per call, so the host pays one ``cudaGraphLaunch`` instead of two copies and five kernel launches through Python.
+        The frame number reaches the kernels through the per-stream frame counters (a device array the graph refreshes from
+        pinned memory), so the captured kernel arguments never change.  Same kernels, same Philox keys: bit-equal to ``step``."""
+        rows = np.asarray(rows, dtype=np.float32)
+        if rows.ndim == 2:
+            rows = rows[:, None, :]
+        nF = rows.shape[1]
+        if rows.shape[0] != self.B or nF > self.nF_max or rows.shape[2] != self.ncols:
+            raise UserWarning(f"rows must be [B={self.B}, nF<={self.nF_max}, {self.ncols}], got {rows.shape}")
+        with torch.cuda.device(self.device):
+            for ev in self.slot_event:                       # nothing submitted earlier may still be using the staging slots
+                if ev is not None:
+                    ev.synchronize()
+            if getattr(self, "_graph", None) is None or self._graph_nF != nF:
+                self._capture_graph(nF)
+            E = self.B * nF
+            self.raw_host[0].view(-1)[: E * self.ncols].view(self.B, nF, self.ncols).numpy()[...] = rows
+            self._graph_frames_host.numpy()[...] = self.frame
+            self._graph.replay()
+            torch.cuda.current_stream().synchronize()
+        msg, std, samples, status = self._host_views(0, nF)
+        out = EstimateBatch(msg, std, samples, status, self.frame)
+        self.frame += nF
+        self.calls += 1
+        self.launches += 2 + self.L
+        return out
+
+    def _capture_graph(self, nF):
+        E = self.B * nF
+        torch.cuda.current_stream().synchronize()
+        stage = self.raw_host[0].view(-1)[: E * self.ncols].view(self.B, nF, self.ncols)
+        raw = self.raw.view(-1)[: E * self.ncols].view(self.B, nF, self.ncols)
+        self._graph_frames_host = torch.zeros(self.B, dtype=torch.int32).pin_memory()
+        self._graph_frames_dev = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        self._graph_frames_host.numpy()[...] = self.frame
+        self._use_out(0)
+        host, dev_out = self.out_host[0], self.out_all
+        saved = (self.frame, self.calls, self.launches)
+
+        def enqueue():
+            self.step_device(raw, nF, _h2d_from=stage, stream_frames=self._graph_frames_dev, _frames_from=self._graph_frames_host,
+                             _out_slot=0, _plain=True)
+            if nF == self.nF_max:
+                host.copy_(dev_out, non_blocking=True)
+            else:
+                Em = self.B * self.nF_max
+                for off, width in ((0, 25), (Em * 25, 6), (Em * 31, 1)) + (((Em * 32, self.S * 6),) if self.emit_samples else ()):
+                    host[off: off + E * width].copy_(dev_out[off: off + E * width], non_blocking=True)
+
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                        # one eager pass first (function attributes, lazy module loading); it
+            enqueue()                                        # recomputes the CURRENT frame from the staged rows, which the replay
+        side.synchronize()                                   # that follows overwrites with the same values
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=side):
+            enqueue()
+        self._graph_nF = nF
+        self.frame, self.calls, self.launches = saved
 
     def _host_views(self, slot, nF):
         host, E, Em = self.out_host[slot].numpy(), self.B * nF, self.B * self.nF_max

@@ -131,7 +131,7 @@ class Estimator:
         """One frame of the loop body (estimator.py:174-176) through the fused path; returns the message."""
         add = self._add_mc_samples if add_mc_samples is None else add_mc_samples
         fe = self._fused_estimator()
-        out = fe.step(np.asarray(row, dtype=np.float32).reshape(1, 1, -1))
+        out = fe.step_graph(np.asarray(row, dtype=np.float32).reshape(1, 1, -1))     # one CUDA-graph launch per frame
         if int(out.status[0, 0]) != 0:
             raise np.linalg.LinAlgError("degenerate 6D rotation (zero or collinear columns)")
         msg = out.msg[0, 0].astype(np.float64)

@@ -435,15 +435,20 @@ def realtime_latency(BatchedEstimator, N, syn, frames=300):
                           stats=spec["stats"], n_streams=1, mc_samples=100, smooth=1, dropout=spec["p"], frames_per_call=1,
                           mask_mode=N.MASK_PHILOX, philox_seed=7)
     rows = syn.synth_rows(kind, 1, frames + 20, config_id=2)
-    lat = []
-    for f in range(frames + 20):
-        t0 = time.perf_counter()
-        be.step(rows[:, f:f + 1])
-        lat.append(time.perf_counter() - t0)
-    lat = np.asarray(lat[20:]) * 1e3
-    return {"workload": "watch+phone pocket LSTM estimator (I22 H256 L2 T6 O14), 1 stream x 100 MC samples, frame by frame",
-            "lstm_variant": be.lstm_variant, "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
-            "frames": frames, "timing": "host wall clock around BatchedEstimator.step (H2D + 3 stages + D2H + sync)"}
+    out = {"workload": "watch+phone pocket LSTM estimator (I22 H256 L2 T6 O14), 1 stream x 100 MC samples, frame by frame",
+           "lstm_variant": be.lstm_variant, "frames": frames}
+    for key, fn, what in (("", be.step_graph, "BatchedEstimator.step_graph (one CUDA-graph launch: H2D + 3 stages + D2H, then sync)"),
+                          ("eager_", be.step, "BatchedEstimator.step (H2D + 3 stages + D2H enqueued call by call, then sync)")):
+        be.reset()
+        lat = []
+        for f in range(frames + 20):
+            t0 = time.perf_counter()
+            fn(rows[:, f:f + 1])
+            lat.append(time.perf_counter() - t0)
+        lat = np.asarray(lat[20:]) * 1e3
+        out.update({key + "p50_ms": float(np.percentile(lat, 50)), key + "p99_ms": float(np.percentile(lat, 99)),
+                    key + "timing": "host wall clock around " + what})
+    return out
 
 
 def main():
