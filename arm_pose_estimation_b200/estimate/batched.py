@@ -431,12 +431,13 @@ class BatchedEstimator:
         return PendingEstimate(self, slot, nF, out.frame0, ev)
 
     # ---- single-call latency path: the whole call as one captured CUDA graph ------------------------------------
-    def step_graph(self, rows):
+    def step_graph(self, rows, stream_frames=None):
         """``step`` for the latency-bound case (a few streams, one call at a time - BASELINE configs[1]): pinned H2D of the rows
         and of the frame counter, the three stages and the pinned D2H are captured ONCE as a CUDA graph and replayed with one
         launch per call, so the host pays one ``cudaGraphLaunch`` instead of two copies and five kernel launches through Python.
         The frame number reaches the kernels through the per-stream frame counters (a device array the graph refreshes from
-        pinned memory), so the captured kernel arguments never change.  Same kernels, same Philox keys: bit-equal to ``step``."""
+        pinned memory), so the captured kernel arguments never change.  Same kernels, same Philox keys: bit-equal to ``step``.
+        ``stream_frames``: optional host int32 ``[B]`` of per-stream frame numbers (negative: no new row), as in ``submit``."""
         rows = np.asarray(rows, dtype=np.float32)
         if rows.ndim == 2:
             rows = rows[:, None, :]
@@ -447,11 +448,15 @@ class BatchedEstimator:
             for ev in self.slot_event:                       # nothing submitted earlier may still be using the staging slots
                 if ev is not None:
                     ev.synchronize()
-            if getattr(self, "_graph", None) is None or self._graph_nF != nF:
-                self._capture_graph(nF)
             E = self.B * nF
+            if getattr(self, "_graph_frames_host", None) is None:
+                self._graph_frames_host = torch.zeros(self.B, dtype=torch.int32).pin_memory()
+                self._graph_frames_dev = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+                self._graph = None
             self.raw_host[0].view(-1)[: E * self.ncols].view(self.B, nF, self.ncols).numpy()[...] = rows
-            self._graph_frames_host.numpy()[...] = self.frame
+            self._graph_frames_host.numpy()[...] = self.frame if stream_frames is None else np.asarray(stream_frames, dtype=np.int32).reshape(self.B)
+            if self._graph is None or self._graph_nF != nF:
+                self._capture_graph(nF)                     # (its eager pass computes THIS call; the replay below repeats it)
             self._graph.replay()
             torch.cuda.current_stream().synchronize()
         msg, std, samples, status = self._host_views(0, nF)
@@ -466,9 +471,6 @@ class BatchedEstimator:
         torch.cuda.current_stream().synchronize()
         stage = self.raw_host[0].view(-1)[: E * self.ncols].view(self.B, nF, self.ncols)
         raw = self.raw.view(-1)[: E * self.ncols].view(self.B, nF, self.ncols)
-        self._graph_frames_host = torch.zeros(self.B, dtype=torch.int32).pin_memory()
-        self._graph_frames_dev = torch.zeros(self.B, dtype=torch.int32, device=self.device)
-        self._graph_frames_host.numpy()[...] = self.frame
         self._use_out(0)
         host, dev_out = self.out_host[0], self.out_all
         saved = (self.frame, self.calls, self.launches)
@@ -485,9 +487,9 @@ class BatchedEstimator:
 
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                        # one eager pass first (function attributes, lazy module loading); it
-            enqueue()                                        # recomputes the CURRENT frame from the staged rows, which the replay
-        side.synchronize()                                   # that follows overwrites with the same values
+        with torch.cuda.stream(side):                        # one eager pass first (function attributes, lazy module loading): it
+            enqueue()                                        # computes the call that is already staged, and the replay that
+        side.synchronize()                                   # follows repeats it with the same inputs and Philox keys
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph, stream=side):
             enqueue()

@@ -101,7 +101,7 @@ class MultiStreamEstimator:
         if not active.any():
             return {}
         stream_frames = np.where(active, self._frames, -1).astype(np.int32)
-        out = self._engine.step(self._rows, stream_frames=stream_frames)
+        out = self._engine.step_graph(self._rows, stream_frames=stream_frames)     # one CUDA-graph launch per tick
         msgs = {}
         for b in np.flatnonzero(active):
             if int(out.status[b, 0]) != 0:
