@@ -27,6 +27,8 @@ class FakeEngine:
         return FakeOut(msg, np.zeros((self.B, 1, 6), np.float32), np.ones((self.B, 1, self.S, 6), np.float32),
                        np.zeros((self.B, 1), np.int32))
 
+    step_graph = step                                       # the front-end ticks through the engine's CUDA-graph entry point
+
 
 def test_collect_applies_the_reference_freshness_policy_per_stream():
     eng = FakeEngine(3)
