@@ -1,9 +1,10 @@
 // Stage 3 kernel: de-normalise the network targets, 6D rotation -> quaternion, forward kinematics through
 // shoulder -> elbow -> hand for every MC / smoothing row, then the per-estimate reduction: sign-aligned
 // quaternion average (transformations.py:32-51), FK again from the averaged quaternions (compose_msg.py:59-61,
-// :92-93), population std of the per-row hand / elbow positions.  HBM-bound: one warp per estimate, lanes
-// stride over the S = smooth * n_samples rows (consecutive lanes read consecutive rows), reductions by
-// warp shuffle, results staged through shared memory so the 25-float message leaves as one coalesced store.
+// :92-93), population std of the per-row hand / elbow positions.  One HALF-WARP per estimate (two estimates per warp: 100 rows are
+// 6.25 passes of 16 lanes instead of 3.1 passes of 32, and every reduction instruction serves two estimates), lanes stride over the
+// S = smooth * n_samples rows (consecutive lanes read consecutive rows), reductions by shuffles inside the half-warp, results staged
+// through shared memory so the 25-float message leaves coalesced.
 #include "ape_fk.cuh"
 
 namespace ape {
@@ -32,15 +33,16 @@ struct FkArgs {
     const float* est_in;      // FROM_EST: [E][S][W] rows of arm_pose_from_nn_targets instead of network targets
 };
 
-__device__ __forceinline__ float warp_sum(float v) {
+constexpr int FK_LANES = 16;                       // lanes per estimate
+
+__device__ __forceinline__ float warp_sum(float v, unsigned m) {          // over the 16 lanes of this half-warp (mask m)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = FK_LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
     return v;
 }
 
-template <typename T> __device__ __forceinline__ Quat<T> bcast0(const Quat<T>& q) {
-    return {__shfl_sync(0xffffffffu, q.w, 0), __shfl_sync(0xffffffffu, q.x, 0), __shfl_sync(0xffffffffu, q.y, 0),
-            __shfl_sync(0xffffffffu, q.z, 0)};
+template <typename T> __device__ __forceinline__ Quat<T> bcast0(const Quat<T>& q, unsigned m, int l0) {   // from the half-warp's lane 0
+    return {__shfl_sync(m, q.w, l0), __shfl_sync(m, q.x, l0), __shfl_sync(m, q.y, l0), __shfl_sync(m, q.z, l0)};
 }
 
 // accumulate q flipped onto the hemisphere of q0 (transformations.py:44-49)
@@ -50,8 +52,8 @@ __device__ __forceinline__ void acc_aligned(Quat<float>& s, const Quat<float>& q
     s.w += sg * q.w; s.x += sg * q.x; s.y += sg * q.y; s.z += sg * q.z;
 }
 
-__device__ __forceinline__ Quat<float> warp_sum_normalised(Quat<float> s) {
-    s.w = warp_sum(s.w); s.x = warp_sum(s.x); s.y = warp_sum(s.y); s.z = warp_sum(s.z);
+__device__ __forceinline__ Quat<float> warp_sum_normalised(Quat<float> s, unsigned m) {
+    s.w = warp_sum(s.w, m); s.x = warp_sum(s.x, m); s.y = warp_sum(s.y, m); s.z = warp_sum(s.z, m);
     const float inv = inv_sqrt(s.w * s.w + s.x * s.x + s.y * s.y + s.z * s.z);
     return {s.w * inv, s.x * inv, s.y * inv, s.z * inv};
 }
@@ -60,7 +62,7 @@ template <int TARGET, bool FROM_EST>
 __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_reduce_kernel(FkArgs a) {
     constexpr int O = TARGET == APE_TARGET_ORI_CAL_LARM_UARM ? 12 : (TARGET == APE_TARGET_ORI_CAL_LARM_UARM_HIPS ? 14 : 20);
     constexpr int W = TARGET == APE_TARGET_ORI_CAL_LARM_UARM ? 14 : 21;
-    __shared__ float s_msg[FK_WARPS_PER_CTA][32];
+    __shared__ float s_msg[FK_WARPS_PER_CTA * 2][32];
     __shared__ float s_m[O], s_s[O];
 
     if (threadIdx.x < O) {
@@ -69,8 +71,10 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
     }
     __syncthreads();
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * FK_WARPS_PER_CTA + warp;
+    const int warp = threadIdx.x >> 5, half = (threadIdx.x >> 4) & 1, lane = threadIdx.x & (FK_LANES - 1);   // lane within the half-warp
+    const unsigned hm = 0xFFFFu << (16 * half);        // this half-warp's lanes: every shuffle / ballot below stays inside it
+    const int l0 = 16 * half;                          // its first lane
+    const int e = (blockIdx.x * FK_WARPS_PER_CTA + warp) * 2 + half;
     const int E = a.B * a.nF;
     if (e >= E) return;
     const int b = e / a.nF;
@@ -91,8 +95,8 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
     float sh0[3] = {0, 0, 0};                      // shoulder of row 0 (S == 1: the message copies row 0)
     bool bad = false;
 
-    int rw = lane / a.n, rs = lane - rw * a.n;        // this lane's row i = rw * n + rs (window frame, MC sample), advanced by 32 per pass
-    for (int i0 = 0; i0 < S; i0 += 32) {
+    int rw = lane / a.n, rs = lane - rw * a.n;        // this lane's row i = rw * n + rs (window frame, MC sample), advanced by 16 per pass
+    for (int i0 = 0; i0 < S; i0 += FK_LANES) {
         const int i = i0 + lane;
         const bool live = i < S;
         RowPose<float> r;
@@ -134,13 +138,13 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
             bad |= rb;
         }
         if (i0 == 0) {                                               // row 0 anchors the sign alignment and the std pivot
-            q0l = bcast0(r.larm); q0u = bcast0(r.uarm); q0h = bcast0(r.hips);
+            q0l = bcast0(r.larm, hm, l0); q0u = bcast0(r.uarm, hm, l0); q0h = bcast0(r.hips, hm, l0);
             const float pv[6] = {r.hand.x, r.hand.y, r.hand.z, r.elbow.x, r.elbow.y, r.elbow.z};
 #pragma unroll
-            for (int j = 0; j < 6; ++j) piv[j] = __shfl_sync(0xffffffffu, pv[j], 0);
-            sh0[0] = __shfl_sync(0xffffffffu, r.shoulder.x, 0);
-            sh0[1] = __shfl_sync(0xffffffffu, r.shoulder.y, 0);
-            sh0[2] = __shfl_sync(0xffffffffu, r.shoulder.z, 0);
+            for (int j = 0; j < 6; ++j) piv[j] = __shfl_sync(hm, pv[j], l0);
+            sh0[0] = __shfl_sync(hm, r.shoulder.x, l0);
+            sh0[1] = __shfl_sync(hm, r.shoulder.y, l0);
+            sh0[2] = __shfl_sync(hm, r.shoulder.z, l0);
         }
         if (live) {
             acc_aligned(sl, r.larm, q0l);
@@ -175,15 +179,15 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
                 if (W == 21) { dst[k++] = r.hips.w; dst[k++] = r.hips.x; dst[k++] = r.hips.y; dst[k++] = r.hips.z; }
             }
         }
-        rs += 32;                                                    // (no integer division per row)
+        rs += FK_LANES;                                              // (no integer division per row)
         while (rs >= a.n) { rs -= a.n; ++rw; }
     }
 
     // ---- reduction over the S rows --------------------------------------------------------------------
     RowPose<float> m;
-    m.larm = warp_sum_normalised(sl);
-    m.uarm = warp_sum_normalised(su);
-    m.hips = TARGET == APE_TARGET_ORI_CAL_LARM_UARM ? Quat<float>{1.0f, 0.0f, 0.0f, 0.0f} : warp_sum_normalised(sh);
+    m.larm = warp_sum_normalised(sl, hm);
+    m.uarm = warp_sum_normalised(su, hm);
+    m.hips = TARGET == APE_TARGET_ORI_CAL_LARM_UARM ? Quat<float>{1.0f, 0.0f, 0.0f, 0.0f} : warp_sum_normalised(sh, hm);
     if (S == 1) {                                                             // copied, not re-normalised
         m.larm = q0l; m.uarm = q0u;
         if (TARGET != APE_TARGET_ORI_CAL_LARM_UARM) m.hips = q0h;
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
     const float invS = 1.0f / (float)S;
     if (TARGET == APE_TARGET_ORI_POS_CAL_LARM_UARM_HIPS) {
 #pragma unroll
-        for (int j = 0; j < 9; ++j) psum[j] = warp_sum(psum[j]) * invS;       // compose_msg.py:27-29
+        for (int j = 0; j < 9; ++j) psum[j] = warp_sum(psum[j], hm) * invS;       // compose_msg.py:27-29
         m.hand = {psum[0], psum[1], psum[2]};
         m.elbow = {psum[3], psum[4], psum[5]};
         m.shoulder = {psum[6], psum[7], psum[8]};
@@ -205,13 +209,13 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
     float sd[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-        const float m1 = warp_sum(d1[j]) * invS, m2 = warp_sum(d2[j]) * invS;
+        const float m1 = warp_sum(d1[j], hm) * invS, m2 = warp_sum(d2[j], hm) * invS;
         sd[j] = sqrtf(fmaxf(m2 - m1 * m1, 0.0f));
     }
-    const unsigned any_bad = __ballot_sync(0xffffffffu, bad);
+    const unsigned any_bad = __ballot_sync(hm, bad) & hm;
 
     if (lane == 0) {
-        float* o = s_msg[warp];                                               // compose_msg.py:67-79 / :100-108
+        float* o = s_msg[warp * 2 + half];                                             // compose_msg.py:67-79 / :100-108
         o[0] = m.larm.w; o[1] = m.larm.x; o[2] = m.larm.y; o[3] = m.larm.z;
         o[4] = m.hand.x; o[5] = m.hand.y; o[6] = m.hand.z;
         o[7] = m.larm.w; o[8] = m.larm.x; o[9] = m.larm.y; o[10] = m.larm.z;
@@ -221,8 +225,8 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
         o[21] = m.hips.w; o[22] = m.hips.x; o[23] = m.hips.y; o[24] = m.hips.z;
         if (a.status) a.status[e] = any_bad ? 1 : 0;
     }
-    __syncwarp();
-    if (lane < 25) a.msg[(size_t)e * 25 + lane] = s_msg[warp][lane];
+    __syncwarp(hm);
+    for (int k = lane; k < 25; k += FK_LANES) a.msg[(size_t)e * 25 + k] = s_msg[warp * 2 + half][k];
     if (a.stdev && lane < 6) {
         float v = sd[0];
 #pragma unroll
@@ -248,7 +252,7 @@ extern "C" int ape_fk_reduce(const float* preds, int pred_ring, const float* yy_
     if (E == 0) return APE_OK;
     if (E > 0x7fffffffLL || (long long)smooth * n_samples > 0x7fffffffLL) return APE_ERR_BAD_ARG;
     FkArgs a{preds, pred_ring, yy_m, yy_s, body9, O, B, nF, frame0, n_samples, smooth, stream_frames, msg, samples, stdev, est_rows, status, nullptr};
-    const int grid = (int)((E + FK_WARPS_PER_CTA - 1) / FK_WARPS_PER_CTA);
+    const int grid = (int)((E + 2 * FK_WARPS_PER_CTA - 1) / (2 * FK_WARPS_PER_CTA));
     cudaStream_t st = (cudaStream_t)stream;
     if (target == APE_TARGET_ORI_CAL_LARM_UARM)
         fk_reduce_kernel<APE_TARGET_ORI_CAL_LARM_UARM, false><<<grid, FK_WARPS_PER_CTA * 32, 0, st>>>(a);
@@ -267,7 +271,7 @@ extern "C" int ape_msg_from_est(const float* est, int W, const float* body9, int
     if (W != (target == APE_TARGET_ORI_CAL_LARM_UARM ? 14 : 21)) return APE_ERR_BAD_ARG;
     if (E == 0) return APE_OK;
     FkArgs a{nullptr, 1, nullptr, nullptr, body9, target_num_outputs(target), E, 1, 0, S, 1, nullptr, msg, nullptr, stdev, nullptr, nullptr, est};
-    const int grid = (E + FK_WARPS_PER_CTA - 1) / FK_WARPS_PER_CTA;
+    const int grid = (E + 2 * FK_WARPS_PER_CTA - 1) / (2 * FK_WARPS_PER_CTA);
     cudaStream_t st = (cudaStream_t)stream;
     if (target == APE_TARGET_ORI_CAL_LARM_UARM)
         fk_reduce_kernel<APE_TARGET_ORI_CAL_LARM_UARM, true><<<grid, FK_WARPS_PER_CTA * 32, 0, st>>>(a);

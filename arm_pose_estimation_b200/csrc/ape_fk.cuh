@@ -56,9 +56,17 @@ template <typename F> APE_HD Quat<F> six_to_quat(const F* c, bool& bad) {
 }
 
 // yaw-only quaternion from (sin, cos): euler_to_quat([0, atan2(s, c), 0]) (transformations.py:177-179)
+// Evaluated without atan2 / sin / cos: with (sy, cy) = (s, c) / |(s, c)| the half angle y / 2 in [-pi/2, pi/2] has
+//   cos(y/2) = sqrt((1 + cy) / 2), sin(y/2) = sy / (2 cos(y/2))              for cy >= 0,
+//   sin(y/2) = sign(s) sqrt((1 - cy) / 2), cos(y/2) = sy / (2 sin(y/2))      for cy < 0
+// (the well-conditioned form on either side; s = c = 0 gives the identity like atan2(0, 0) = 0).
 template <typename F> APE_HD Quat<F> hips_quat(F s, F c) {
-    const F y = atan2(s, c);
-    return {cos(y * F(0.5)), F(0), sin(y * F(0.5)), F(0)};
+    const F n2 = s * s + c * c;
+    if (!(n2 > F(0))) return {F(1), F(0), F(0), F(0)};
+    const F ir = inv_sqrt(n2), cy = c * ir, sy = s * ir;
+    const F a = F(0.5) * (F(1) + (cy < F(0) ? -cy : cy)), ia = inv_sqrt(a);          // a in [0.5, 1]
+    const F big = a * ia, small = F(0.5) * (sy < F(0) ? -sy : sy) * ia;              // sqrt(a), |sy| / (2 sqrt(a))
+    return cy >= F(0) ? Quat<F>{big, F(0), copysign(small, s), F(0)} : Quat<F>{small, F(0), copysign(big, s), F(0)};
 }
 
 template <typename F> struct Body {
