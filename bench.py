@@ -380,6 +380,9 @@ def fk_standalone(N, syn, torch, kind, n, peaks, E=32768, reps=20):
     return {"kernel": "fk_reduce_kernel (stage 3 standalone)", "estimates": E, "mc_rows": n, "ms_per_launch": ms,
             "bytes_per_estimate": bytes_per_est, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": gbs / peaks["hbm_gbs"], "estimates_per_s": E / (ms * 1e-3),
+            # DRAM bytes of one launch from the committed ncu capture (profiles/r1i_ncu_summary.md, last section: 157.3 MB read + 54.6 MB
+            # written - part of the 83 MB of results is still in the L2 when the kernel ends); only for the captured shape
+            "traffic": (157.311744e6 + 54.591232e6) if (E == 32768 and n == 100 and O == 12) else None,
             "l2": f"{E * bytes_per_est / 1e6:.0f} MB per launch: larger than the 126 MB L2"}
 
 
