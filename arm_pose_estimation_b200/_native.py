@@ -22,9 +22,9 @@ KSLICE = 16                      # csrc/ape_lstm_pack.h: APE_KSLICE
 
 # every symbol include/ape_b200.h declares (tests/test_cabi.py checks the header against this list and the .so)
 SYMBOLS = (
-    "ape_abi_version", "ape_last_cuda_error", "ape_device_info", "ape_lstm_blob_floats", "ape_features",
+    "ape_abi_version", "ape_last_cuda_error", "ape_device_info", "ape_lstm_blob_floats", "ape_features", "ape_features_push",
     "ape_mc_lstm_workspace_bytes", "ape_mc_lstm_fma", "ape_mc_lstm_tc_supported", "ape_lstm_tc_blob_bytes",
-    "ape_mc_lstm_tc_workspace_bytes", "ape_mc_lstm_tc", "ape_philox_masks", "ape_ff_blob_floats", "ape_mc_ff", "ape_dense_act", "ape_fk_reduce", "ape_msg_from_est",
+    "ape_mc_lstm_tc_workspace_bytes", "ape_mc_lstm_tc_workspace_bytes_all_steps", "ape_mc_lstm_tc", "ape_mc_lstm_tc_launch_count", "ape_philox_masks", "ape_ff_blob_floats", "ape_mc_ff", "ape_dense_act", "ape_fk_reduce", "ape_msg_from_est",
     "ape_selfcheck_philox", "ape_selfcheck_keep8", "ape_selfcheck_features", "ape_selfcheck_row_pose", "ape_selfcheck_tcs_schedule",
     "ape_selftest_umma",
 )
@@ -55,6 +55,10 @@ class LstmArgs(C.Structure):
         ("trace", C.c_void_p),
         ("trace_layer", C.c_int),
         ("stream_frames", C.c_void_p),
+        ("ws_E", C.c_int),
+        ("tc_flags", C.c_int),
+        ("h0", C.c_void_p),
+        ("c0", C.c_void_p),
     ]
 
 
@@ -86,6 +90,8 @@ def load():
     lib.ape_lstm_blob_floats.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_int64)]
     lib.ape_features.restype = i32
     lib.ape_features.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, vp, i32, vp]
+    lib.ape_features_push.restype = i32
+    lib.ape_features_push.argtypes = [vp, i32, vp, vp, i32, vp, i32, i32, vp, i32, vp]
     lib.ape_mc_lstm_workspace_bytes.restype = i32
     lib.ape_mc_lstm_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(u64)]
     lib.ape_mc_lstm_fma.restype = i32
@@ -96,8 +102,12 @@ def load():
     lib.ape_lstm_tc_blob_bytes.argtypes = [i32, i32, i32, C.POINTER(C.c_int64)]
     lib.ape_mc_lstm_tc_workspace_bytes.restype = i32
     lib.ape_mc_lstm_tc_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(u64)]
+    lib.ape_mc_lstm_tc_workspace_bytes_all_steps.restype = i32
+    lib.ape_mc_lstm_tc_workspace_bytes_all_steps.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(u64)]
     lib.ape_mc_lstm_tc.restype = i32
     lib.ape_mc_lstm_tc.argtypes = [C.POINTER(LstmArgs), vp]
+    lib.ape_mc_lstm_tc_launch_count.restype = i32
+    lib.ape_mc_lstm_tc_launch_count.argtypes = [C.POINTER(LstmArgs), C.POINTER(i32)]
     lib.ape_philox_masks.restype = i32
     lib.ape_philox_masks.argtypes = [u64, u32, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp]
     lib.ape_ff_blob_floats.restype = i32
@@ -159,9 +169,11 @@ def blob_floats(I, H, L, O):
     return out.value
 
 
-def workspace_bytes(I, H, L, T, O, E, n, tensor_core=False):
+def workspace_bytes(I, H, L, T, O, E, n, tensor_core=False, all_steps=False):
     out = C.c_uint64(0)
-    if tensor_core:
+    if tensor_core and all_steps:
+        check(load().ape_mc_lstm_tc_workspace_bytes_all_steps(I, H, L, T, O, E, n, C.byref(out)), "ape_mc_lstm_tc_workspace_bytes_all_steps")
+    elif tensor_core:
         check(load().ape_mc_lstm_tc_workspace_bytes(I, H, L, T, O, E, n, C.byref(out)), "ape_mc_lstm_tc_workspace_bytes")
     else:
         check(load().ape_mc_lstm_workspace_bytes(I, H, L, T, O, E, n, C.byref(out)), "ape_mc_lstm_workspace_bytes")

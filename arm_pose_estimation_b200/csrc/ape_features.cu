@@ -43,7 +43,33 @@ features_kernel(const float* __restrict__ raw, int layout, int kind, const doubl
     }
 }
 
+// The second of the reference's three per-frame calls handed an already-parsed feature row (estimator.py:93-104): z-score it and
+// put it into the stream's feature ring at the stream's frame, exactly where features_kernel would have put it.
+__global__ void features_push_kernel(const double* __restrict__ xx, int I, const double* __restrict__ xx_m,
+                                     const double* __restrict__ xx_s, int normalize, float* __restrict__ feats, int B,
+                                     int frame0, const int32_t* __restrict__ stream_frames, int feat_ring) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * I) return;
+    const int b = idx / I, j = idx - b * I;
+    const int f = stream_frames ? stream_frames[b] : frame0;
+    if (f < 0) return;
+    const double v = normalize ? (xx[idx] - xx_m[j]) / xx_s[j] : xx[idx];
+    feats[((size_t)b * feat_ring + (f % feat_ring)) * I + j] = (float)v;
+}
+
 }  // namespace ape
+
+extern "C" int ape_features_push(const double* xx, int I, const double* xx_m, const double* xx_s, int normalize, float* feats,
+                                 int B, int frame0, const int32_t* stream_frames, int feat_ring, void* stream) {
+    using namespace ape;
+    if (!xx || !feats || I < 1 || B < 0 || frame0 < 0 || feat_ring < 1) return APE_ERR_BAD_ARG;
+    if (normalize && (!xx_m || !xx_s)) return APE_ERR_BAD_ARG;
+    if (B == 0) return APE_OK;
+    if ((long long)B * I > 0x7fffffffLL) return APE_ERR_BAD_ARG;
+    const int threads = 128, grid = (B * I + threads - 1) / threads;
+    features_push_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(xx, I, xx_m, xx_s, normalize, feats, B, frame0, stream_frames, feat_ring);
+    return check_launch();
+}
 
 extern "C" int ape_features(const float* raw, int layout, int kind, const double* xx_m, const double* xx_s,
                             int normalize, float* feats, int B, int nF, int frame0, const int32_t* stream_frames, int feat_ring,

@@ -46,6 +46,8 @@ struct LayerArgs {
     int O;
     float* preds;
     int pred_ring, all_steps, n_out;
+    const float* h0;          // optional initial state of this layer, [rows][H] each (torch.nn.LSTM(x, (h_0, c_0))), or null
+    const float* c0;
 };
 
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -71,8 +73,9 @@ template <int RT> __device__ __forceinline__ void st_vec(float* p, const float* 
 // position of the weight-slice stream: (time step, N-chunk, K-slice)
 struct SliceCursor {
     int t, chunk, ks;
+    bool state0;                                               // a caller-supplied h_0: step 0 has a recurrent half too
     __device__ __forceinline__ void advance(int nsx, int nsh, int nchunks) {
-        const int ns = nsx + (t > 0 ? nsh : 0);                 // h_{-1} = 0: step 0 skips the recurrent slices
+        const int ns = nsx + ((t > 0 || state0) ? nsh : 0);     // h_{-1} = 0: step 0 skips the recurrent slices
         if (++ks == ns) { ks = 0; if (++chunk == nchunks) { chunk = 0; ++t; } }
     }
 };
@@ -110,7 +113,27 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerAr
         cp_async_commit();
     };
 
-    SliceCursor pf{0, 0, 0};                        // prefetch cursor runs W_STAGES-1 slices ahead
+    const bool state0 = a.h0 != nullptr;
+    if (state0) {                                   // (h_0, c_0) of nn_models.py:180-189 instead of zeros
+        for (int idx = tid; idx < H * R; idx += LSTM_THREADS) {
+            const int r = idx % R, k = idx / R, row = row0 + r;
+            hbuf[k * R + r] = row < a.rows ? __ldg(a.h0 + (size_t)row * H + k) : 0.0f;
+            if (NCH_REG == 0) cbuf[k * R + r] = row < a.rows ? __ldg(a.c0 + (size_t)row * H + k) : 0.0f;
+        }
+        if (NCH_REG > 0) {
+#pragma unroll
+            for (int chunk = 0; chunk < (NCH_REG > 0 ? NCH_REG : 1); ++chunk)
+#pragma unroll
+                for (int half = 0; half < 2; ++half)
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const int row = row0 + rg * RT + r;
+                        creg[chunk][half][r] = row < a.rows ? __ldg(a.c0 + (size_t)row * H + chunk * CHUNK_UNITS + cg + 16 * half) : 0.0f;
+                    }
+        }
+        __syncthreads();
+    }
+    SliceCursor pf{0, 0, 0, state0};                // prefetch cursor runs W_STAGES-1 slices ahead
     for (int s = 0; s < W_STAGES - 1; ++s) { issue_slice(pf, s); pf.advance(nsx, nsh, nchunks); }
     int slice = 0, cur = 0;
 
@@ -175,7 +198,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerAr
 
         const float* hcur = hbuf + cur * H * R;
         float* hnxt = hbuf + (cur ^ 1) * H * R;
-        const int ns = nsx + (t > 0 ? nsh : 0);
+        const int ns = nsx + ((t > 0 || state0) ? nsh : 0);
 
         auto chunk_body = [&](const int chunk, float (&cst)[2][RT]) {
             float acc[RT][8];
@@ -218,14 +241,14 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerAr
                 if (NCH_REG > 0) {
 #pragma unroll
                     for (int r = 0; r < RT; ++r) cv[r] = cst[half][r];
-                } else if (t > 0) {
+                } else if (t > 0 || state0) {
                     ld_vec<RT>(cbuf + u * R + rg * RT, cv);
                 }
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
                     const float gi = sigmoid_f(acc[r][4 * half + 0]), gf = sigmoid_f(acc[r][4 * half + 1]);
                     const float gg = tanh_f(acc[r][4 * half + 2]), go = sigmoid_f(acc[r][4 * half + 3]);
-                    const float c = t > 0 ? fmaf(gf, cv[r], gi * gg) : gi * gg;
+                    const float c = (t > 0 || state0) ? fmaf(gf, cv[r], gi * gg) : gi * gg;
                     cv[r] = c;
                     hv[r] = go * tanh_f(c);
                 }
@@ -360,6 +383,11 @@ int check_lstm_args(const ape_lstm_args* g) {
     if (g->mask_mode == APE_MASK_INJECTED && g->L > 1 && !g->masks) return APE_ERR_BAD_ARG;
     if (g->mask_mode != APE_MASK_NONE && !(g->dropout_p >= 0.0f && g->dropout_p < 1.0f)) return APE_ERR_BAD_ARG;
     if ((long long)g->B * g->nF * g->n_samples > 0x7fffffffLL) return APE_ERR_BAD_ARG;
+    // the Philox counter packs sample (20 bits), gap (4 bits) and step (8 bits) into one word (ape_common.cuh): beyond these
+    // ranges masks of different steps / gaps / samples would alias
+    if (g->mask_mode == APE_MASK_PHILOX && g->L > 1 && (g->T > 256 || g->L > 16 || g->n_samples > (1 << 20))) return APE_ERR_UNSUPPORTED;
+    if ((g->h0 == nullptr) != (g->c0 == nullptr)) return APE_ERR_BAD_ARG;
+    if (g->h0 && g->n_samples != 1) return APE_ERR_UNSUPPORTED;
     return APE_OK;
 }
 
@@ -398,6 +426,10 @@ int fma_launch_layer(const ape_lstm_args* g, int l, const FmaPlan& p, const floa
     }
     a.out_seq = last ? nullptr : seq_out;
     a.preds = last ? g->preds : nullptr;
+    if (g->h0) {                                    // [L][E][H]; n_samples == 1, so every layer has E rows
+        a.h0 = g->h0 + (size_t)l * E * g->H;
+        a.c0 = g->c0 + (size_t)l * E * g->H;
+    }
     return launch_layer_rt(rt, a, tiles, st);
 }
 

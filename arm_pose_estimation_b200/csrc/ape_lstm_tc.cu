@@ -498,6 +498,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
     if (warp == MMA_WARP) tmem_dealloc<2>(tmem, TMEM_COLS);
 }
 
+// all_steps (the model API, DropoutLSTM.forward / monte_carlo_predictions): the output layer on EVERY step of the last layer's
+// sequence.  units: [pair tile][T][cta][H/8][128 rows] 16-byte units of fp16 h_t (unscaled); Wo: [O][H] then bias [O];
+// preds: [row][T][O] float32.  One thread per output value; rows x T x O x H multiply-adds, negligible next to the layers.
+__global__ void units_output_kernel(const uint4* __restrict__ units, const float* __restrict__ Wo, float* __restrict__ preds,
+                                    int rows, int T, int H, int O) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * T * O) return;
+    const int o = (int)(idx % O), t = (int)((idx / O) % T), row = (int)(idx / ((long long)O * T));
+    const int tile = row >> 8, cta = (row >> 7) & 1, r = row & 127, KG = H / 8;
+    const uint4* src = units + ((((size_t)tile * T + t) * 2 + cta) * KG) * ROWS + r;
+    const float* w = Wo + (size_t)o * H;
+    float sum = __ldg(Wo + (size_t)O * H + o);
+    for (int j = 0; j < KG; ++j) {
+        const uint4 u = __ldg(src + (size_t)j * ROWS);
+        const uint32_t v[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v[k]));
+            sum = fmaf(__ldg(w + 8 * j + 2 * k), f.x, sum);
+            sum = fmaf(__ldg(w + 8 * j + 2 * k + 1), f.y, sum);
+        }
+    }
+    preds[idx] = sum;
+}
+
 template <int H> static size_t smem_bytes(int kgx) {
     return 3 * (size_t)(H / 8) * ROWS * 16 + 4 * H * sizeof(float) + BAR_BLOCK_BYTES + (size_t)(H / 32) * (kgx + H / 8) * 64 * 16;
 }
@@ -540,15 +565,62 @@ extern "C" int ape_mc_lstm_tc_supported(int I, int H, int L, int O) {
             ape_pack_kin_pad(0, I, H) <= H && O >= 1) ? 1 : 0;
 }
 
+// Workspace layout of the tensor-core path, computed from the LARGEST call that will use the workspace (ws_E) so that calls of
+// different sizes in flight on different streams agree on every offset:
+//   [2 x scratch region][layer 0 output, copy 0][copy 1][units of layers >= 1, up to 2 buffers (+ 1 for all_steps)]
+struct TcWsLayout { size_t scratch_region, u0, u1, total; };
+static size_t tc_u0_bytes(long long E, int T, int H) {
+    const unsigned long long rpc0 = tc_rpc0(E), tiles0 = ((unsigned long long)E + 2 * rpc0 - 1) / (2 * rpc0);
+    return (size_t)((tiles0 * 256 * T * H * 2 + 255) & ~(unsigned long long)255);
+}
+static TcWsLayout tc_ws_layout(int H, int L, int T, long long E, int n_samples, bool all_steps) {
+    TcWsLayout w{};
+    // a short call (< 512 estimates) spreads layer 0 over 32-row CTAs and needs up to 4x the row slots per estimate
+    w.u0 = tc_u0_bytes(E, T, H);
+    if (E > 511) { const size_t small = tc_u0_bytes(511, T, H); if (small > w.u0) w.u0 = small; }
+    const unsigned long long tiles1 = ((unsigned long long)E * n_samples + 255) / 256;
+    w.u1 = (size_t)((tiles1 * 256 * T * H * 2 + 255) & ~(unsigned long long)255);
+    // per-CTA cell-state scratch: two regions (layer 0 of the next call may run on a side stream under a layer >= 1 of this one);
+    // streamed-weights kernel (H = 256) and two-layer wavefront kernel (H = 128, L >= 3)
+    w.scratch_region = ape::tcs::scratch_bytes(H, TC_MAX_SMS);
+    if (L >= 3) { const size_t s2 = ape::tcw::scratch_bytes(H, TC_MAX_SMS); if (s2 > w.scratch_region) w.scratch_region = s2; }
+    const int n_u1 = L - 2 + (all_steps ? 1 : 0);
+    w.total = 2 * w.scratch_region + 2 * w.u0 + (size_t)(n_u1 > 2 ? 2 : (n_u1 < 0 ? 0 : n_u1)) * w.u1 + 512;
+    return w;
+}
+
 extern "C" int ape_mc_lstm_tc_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes) {
     if (!bytes || I < 1 || H < 1 || L < 1 || T < 1 || O < 1 || E < 0 || n_samples < 1) return APE_ERR_BAD_ARG;
     if (!ape_mc_lstm_tc_supported(I, H, L, O)) return APE_ERR_UNSUPPORTED;
-    const uint64_t rpc0 = tc_rpc0(E);
-    const uint64_t tiles0 = ((uint64_t)E + 2 * rpc0 - 1) / (2 * rpc0), tiles1 = ((uint64_t)E * n_samples + 255) / 256;
-    const uint64_t u0 = (tiles0 * 256 * T * H * 2 + 255) & ~(uint64_t)255, u1 = (tiles1 * 256 * T * H * 2 + 255) & ~(uint64_t)255;
-    *bytes = 2 * u0 + (L > 3 ? 2 : (L > 2 ? 1 : 0)) * u1 + 512;            // two copies of layer 0's output (ws_parity)
-    // streamed-weights kernel: two regions of per-CTA cell-state scratch (layer 0 may run on a side stream under a layer >= 1)
-    *bytes += 2 * (uint64_t)ape::tcs::scratch_bytes(H, TC_MAX_SMS);
+    *bytes = tc_ws_layout(H, L, T, E, n_samples, false).total;
+    return APE_OK;
+}
+
+// the same for a call with all_steps != 0 (the model API: the last layer's sequence is kept for the per-step output layer)
+extern "C" int ape_mc_lstm_tc_workspace_bytes_all_steps(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes) {
+    if (!bytes || I < 1 || H < 1 || L < 1 || T < 1 || O < 1 || E < 0 || n_samples < 1) return APE_ERR_BAD_ARG;
+    if (!ape_mc_lstm_tc_supported(I, H, L, O)) return APE_ERR_UNSUPPORTED;
+    *bytes = tc_ws_layout(H, L, T, E, n_samples, true).total;
+    return APE_OK;
+}
+
+static bool tc_pairs_layers(const ape_lstm_args* g, long long tiles1, int sm_count) {
+    return ape::tcw::supported(g->H, g->T, g->O) && g->tc_flags != 1 && (g->tc_flags == 2 || tiles1 >= sm_count / 2);
+}
+
+// kernels ape_mc_lstm_tc will launch for these arguments (bench.py's gpu_launches; depends on the pairing rule above)
+extern "C" int ape_mc_lstm_tc_launch_count(const ape_lstm_args* g, int* launches) {
+    if (!g || !launches) return APE_ERR_BAD_ARG;
+    int dev = 0, sm_count = 0;
+    APE_CUDA_TRY(cudaGetDevice(&dev));
+    APE_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    const long long rows = (long long)g->B * g->nF * g->n_samples;
+    const int l_begin = (g->layer_begin == 0 && g->layer_end == 0) ? 0 : g->layer_begin;
+    const int l_end = (g->layer_begin == 0 && g->layer_end == 0) ? g->L : g->layer_end;
+    const bool pair_ok = tc_pairs_layers(g, (rows + 255) / 256, sm_count);
+    int n = 0;
+    for (int l = l_begin; l < l_end;) { ++n; l += (pair_ok && l >= 1 && l + 1 < l_end) ? 2 : 1; }
+    *launches = n + (g->all_steps ? 1 : 0);
     return APE_OK;
 }
 
@@ -556,7 +628,9 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
     using namespace ape;
     int rc = check_lstm_args(g);
     if (rc != APE_OK) return rc;
-    if (!ape_mc_lstm_tc_supported(g->I, g->H, g->L, g->O) || g->all_steps) return APE_ERR_UNSUPPORTED;
+    if (!ape_mc_lstm_tc_supported(g->I, g->H, g->L, g->O)) return APE_ERR_UNSUPPORTED;
+    if (g->all_steps && (g->layer_begin != 0 || g->layer_end != 0)) return APE_ERR_UNSUPPORTED;
+    if (g->h0 || g->c0) return APE_ERR_UNSUPPORTED;            // a caller-supplied initial state runs on the fp32 path
     if (g->T > 40) return APE_ERR_UNSUPPORTED;                 // |c_t| <= t keeps 2^(2 c log2e) finite in fp32 only for T <= 44
     if (!g->weights_tc) return APE_ERR_BAD_ARG;
     const long long E = (long long)g->B * g->nF;
@@ -570,20 +644,22 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
     const long long rows = E * g->n_samples;
     const int rpc0 = tc_rpc0(E);
     const int tiles0 = (int)((E + 2 * rpc0 - 1) / (2 * rpc0)), tiles1 = (int)((rows + 255) / 256);
-    const size_t u0 = ((size_t)tiles0 * 256 * g->T * g->H * 2 + 255) & ~(size_t)255;
-    const size_t u1 = ((size_t)tiles1 * 256 * g->T * g->H * 2 + 255) & ~(size_t)255;
+    if (g->ws_E != 0 && g->ws_E < E) return APE_ERR_BAD_ARG;
+    const TcWsLayout wl_ = tc_ws_layout(g->H, g->L, g->T, g->ws_E > 0 ? g->ws_E : E, g->n_samples, g->all_steps != 0);
+    const size_t u0 = wl_.u0, u1 = wl_.u1;
     char* wsp = (char*)(((uintptr_t)g->workspace + 255) & ~(uintptr_t)255);
-    // streamed-weights kernel (H = 256): two regions of per-CTA cell-state scratch at the front (a position that does not
-    // depend on the call's size: layer 0 of the next call may run on a side stream under a layer >= 1 of this one)
+    // per-CTA cell-state scratch at the front (a position that does not depend on the call's size)
     char* scratch = wsp;
-    const size_t scratch_region = tcs::scratch_bytes(g->H, TC_MAX_SMS);
+    const size_t scratch_region = wl_.scratch_region;
     if (scratch_region && sm_count > TC_MAX_SMS) return APE_ERR_UNSUPPORTED;
     wsp += 2 * scratch_region;
     uint4* units0 = (uint4*)(wsp + (g->ws_parity & 1) * u0);            // layer 0 output, one row per estimate (two copies)
-    uint4* units[2] = {(uint4*)(wsp + 2 * u0), (uint4*)(wsp + 2 * u0 + u1)};   // layers >= 1 outputs, one row per (estimate, sample)
+    // layers >= 1 outputs, one row per (estimate, sample) (all_steps: the last layer's sequence is kept too, for the per-step output layer)
+    uint4* units[2] = {(uint4*)(wsp + 2 * u0), (uint4*)(wsp + 2 * u0 + u1)};
     const int l_begin = (g->layer_begin == 0 && g->layer_end == 0) ? 0 : g->layer_begin;
     const int l_end = (g->layer_begin == 0 && g->layer_end == 0) ? g->L : g->layer_end;
     if (l_begin < 0 || l_end > g->L || l_begin >= l_end) return APE_ERR_BAD_ARG;
+    if (g->tc_flags < 0 || g->tc_flags > 2) return APE_ERR_BAD_ARG;
 
     cudaEvent_t ev[17] = {};
     const bool prof = g->layer_ms != nullptr && g->L <= 16 && l_begin == 0 && l_end == g->L;
@@ -595,13 +671,13 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
     const uint8_t* wo16 = wl;                                               // the fp16 output-layer tile sits after all layers
     for (int l = 0; l < g->L; ++l) wo16 += tc_layer_bytes(l, g->I, g->H);
     const float scale = g->mask_mode == APE_MASK_NONE ? 1.0f : 1.0f / (1.0f - g->dropout_p);
-    for (int l = 0; l < l_end; ++l) {
+    const bool all_steps = g->all_steps != 0;
+    // argument block of layer l (`wl_l`: its weights inside the fp16 blob)
+    auto layer_args = [&](int l, const uint8_t* wl_l) {
         const bool last = l == g->L - 1;
         tc::TcLayerArgs a{};
-        a.W = wl;
-        a.bias_s = (const float*)(wl + tc_layer_bytes(l, g->I, H) - (size_t)4 * H * 4);
-        wl += tc_layer_bytes(l, g->I, H);
-        if (l < l_begin) continue;
+        a.W = wl_l;
+        a.bias_s = (const float*)(wl_l + tc_layer_bytes(l, g->I, H) - (size_t)4 * H * 4);
         a.T = g->T;
         a.kgx = tc_kgx(l, g->I, H);
         a.Kin = l == 0 ? g->I : H;
@@ -622,26 +698,56 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
             a.in_rpc_shift = rpc0 == 128 ? 7 : 5;
             a.n_pair_tiles = tiles1;
             a.mask_mode = g->mask_mode;
-            a.out_units = last ? nullptr : units[(l - 1) & 1];
+            a.out_units = (last && !all_steps) ? nullptr : units[(l - 1) & 1];
         }
         a.masks = g->masks; a.gap = l - 1; a.n_gaps = g->L - 1;
         a.seed = g->philox_seed; a.stream_id0 = g->stream_id0;
         a.rk = philox_round_keys(g->philox_seed);
         a.keep_thr16 = keep_threshold16(g->dropout_p);
-        a.out_scale = scale;                                            // the next layer's dropout scale, applied before rounding
+        // the next layer's dropout scale, applied before the fp16 rounding (all_steps: the last layer's sequence feeds the output layer as is)
+        a.out_scale = last ? 1.0f : scale;
         a.Wo = g->weights + ape_pack_out_offset(g->I, g->H, g->L);
         a.bo = a.Wo + (size_t)g->O * g->H;
         a.O = g->O;
         a.Wo16 = wo16;
-        a.preds = last ? g->preds : nullptr;
+        a.preds = (last && !all_steps) ? g->preds : nullptr;
         a.pred_ring = g->pred_ring; a.n_out = g->n_samples;
         a.cstate = scratch_region ? (float*)(scratch + (l == 0 ? 0 : scratch_region)) : nullptr;
         a.trace = (g->trace && l == g->trace_layer) ? (long long*)g->trace : nullptr;
         // trace_layer < 0: the CTA timeline of every layer instead, [layer][TC_MAX_SMS CTAs][4]
         a.timeline = (g->trace && g->trace_layer < 0) ? (long long*)g->trace + (size_t)l * TC_MAX_SMS * 4 : nullptr;
+        return a;
+    };
+    // Two consecutive layers >= 1 of an H = 128 model run as ONE wavefront launch (ape_lstm_tcw.cu) when the batch gives every
+    // CTA pair at least one tile (below that a lone tile is faster through two one-layer launches: its two layers cannot overlap
+    // on the epilogue warps of one pair); tc_flags forces either way.
+    const bool pair_ok = tc_pairs_layers(g, tiles1, sm_count);
+    for (int l = 0; l < l_end;) {
+        const uint8_t* wl_l = wl;
+        wl += tc_layer_bytes(l, g->I, H);
+        if (l < l_begin) { ++l; continue; }
+        const tc::TcLayerArgs a = layer_args(l, wl_l);
+        if (pair_ok && l >= 1 && l + 1 < l_end) {
+            const tc::TcLayerArgs b = layer_args(l + 1, wl);
+            wl += tc_layer_bytes(l + 1, g->I, H);
+            rc = tcw::launch_pair(a, b, sm_count, st);
+            if (rc != APE_OK) return rc;
+            if (prof) { APE_CUDA_TRY(cudaEventRecord(ev[l + 1], st)); APE_CUDA_TRY(cudaEventRecord(ev[l + 2], st)); }   // layer_ms[l] = the pair, [l+1] = 0
+            l += 2;
+            continue;
+        }
         rc = H == 128 ? tc::launch<128>(a, sm_count, st) : H == 64 ? tc::launch<64>(a, sm_count, st) : tcs::launch_layer(H, a, sm_count, st);
         if (rc != APE_OK) return rc;
         if (prof) APE_CUDA_TRY(cudaEventRecord(ev[l + 1], st));
+        ++l;
+    }
+    if (all_steps) {                                            // output layer on every step (nn_models.py:189: output_layer(all))
+        const long long total = rows * g->T * g->O;
+        const int threads = 256;
+        tc::units_output_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
+            units[(g->L - 2) & 1], g->weights + ape_pack_out_offset(g->I, g->H, g->L), g->preds, (int)rows, g->T, H, g->O);
+        rc = check_launch();
+        if (rc != APE_OK) return rc;
     }
     if (prof) {
         APE_CUDA_TRY(cudaStreamSynchronize(st));

@@ -110,4 +110,11 @@ bool supported(int H);
 size_t scratch_bytes(int H, int sm_count);      // one region of per-CTA cell-state scratch (a launch needs one)
 int launch_layer(int H, const tc::TcLayerArgs& a, int sm_count, cudaStream_t st);
 }  // namespace tcs
+
+namespace tcw {
+// two-layer wavefront kernel (ape_lstm_tcw.cu): layers a and b = a + 1 of an H = 128 model in one launch
+bool supported(int H, int T, int O);
+size_t scratch_bytes(int H, int sm_count);      // per-CTA cell-state scratch of one launch
+int launch_pair(const tc::TcLayerArgs& a, const tc::TcLayerArgs& b, int sm_count, cudaStream_t st);
+}  // namespace tcw
 }  // namespace ape

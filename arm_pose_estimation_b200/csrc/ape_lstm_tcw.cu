@@ -1,0 +1,537 @@
+// Stage 2, tensor-core variant for H = 128, TWO consecutive layers >= 1 of the MC-dropout LSTM in ONE launch: a wavefront.
+//
+// The one-layer kernel (ape_lstm_tc.cu) keeps a layer's gate weights resident in shared memory and runs ONE recurrence per
+// CTA pair: every gate pre-activation of step t+1 needs all of h_t, so each step ends in a barrier over the pair's 32
+// epilogue warps (their skew + the publish -> MMA -> commit -> load latency: 16 % of the epilogue warps' time), and the
+// sequence between two layers round-trips HBM (157 MB per layer at 1024 streams x 100 samples).  Here a CTA pair carries
+// layers A = l and B = l+1 of the same 256-row tile side by side, B one step behind A:
+//
+//     wave w:   A computes step (tile, t) = item w        B computes item w-1
+//
+// A's step only needs what A produced one wave earlier, B's step needs A's h of the previous wave (its input x2 = dropout(h_A))
+// and its own h of the previous wave - so while the epilogue warps run the cell update of one layer, the tensor pipe
+// already works on the other layer's gates, and nothing ever waits on a result that was produced less than half a wave ago.
+// Items run on across tile boundaries (A starts the next tile while B finishes the last step of the previous one), so a
+// launch pays one half-wave of fill and drain in total.
+//
+// What lives where (per CTA = 128 rows; one row per TMEM lane):
+//   * gate weights of BOTH layers (2 x 128 KB per CTA) stream from L2 through a shared-memory ring of 16 KB slots filled by one
+//     thread with bulk asynchronous copies (cp.async.bulk, mbarrier complete_tx; as in ape_lstm_tcs.cu).  A piece is one
+//     operand half (x- or recurrent part, K = 128) of this CTA's 64 gate columns of a 32-unit chunk = 8 MMAs;
+//   * accumulators: two 128-column TMEM slots, used alternately by the chunk sequence A0..A3, B0..B3, A0.. (one issuer warp
+//     per slot); h_A and h_B as packed fp16 pairs in TMEM (2 x 64 columns each, written with tcgen05.st), A operand of the
+//     recurrent MMAs ([a_tmem] form);
+//   * x1 (layer A's input: the previous layer's fp16 units, dropout mask ANDed in by the loader warps) and x2 = dropout(h_A)
+//     (written by the epilogue warps as they produce h_A; double-buffered by item parity) are shared-memory operand tiles;
+//   * the dropout keep-bits of x2 are drawn by the LOADER warps one wave ahead (Philox, or the injected bytes) and handed to
+//     the epilogue as one 32-bit word per (row, 8 units) in shared memory; the epilogue expands it with 4 PRMT (sign-replicate);
+//   * the fp32 cell states (2 x 32 values per thread) live in a per-CTA 128 KB scratch that stays in L2, prefetched one
+//     half-pass ahead (as in ape_lstm_tcs.cu);
+//   * the inter-layer sequence never touches HBM.
+// Arithmetic, operand rounding points and Philox keys are those of ape_lstm_tc.cu: results are identical.
+#include "ape_common.cuh"
+#include "ape_lstm_pack.h"
+#include "ape_lstm_tc_args.cuh"
+#include "ape_umma.cuh"
+
+namespace ape {
+namespace tcw {
+
+using tc::TcLayerArgs;
+using tc::tanh_approx;
+
+constexpr int H = 128, NCHL = H / 32, KG = H / 8;  // chunks per layer, k-groups per operand
+constexpr int EPI_WARPS = 16, LOAD_WARPS = 4;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS;   // leader CTA: two MMA issuers (issuer k owns accumulator slot k);
+constexpr int N_ISSUERS = 2;                       //   peer CTA: the first of them forwards "piece landed" to the leader
+constexpr int TMA_WARP = MMA_WARP + N_ISSUERS;     // one lane per CTA fills the weight ring
+constexpr int THREADS = (TMA_WARP + 1) * 32;       // 736
+constexpr int ROWS = 128;
+constexpr uint32_t KG_BYTES_B = 64 * 16;           // one k-group of a 64-column weight tile
+constexpr uint32_t PIECE_BYTES = KG * KG_BYTES_B;  // 16 KB: one operand half of one chunk = one ring slot
+constexpr uint32_t CHUNK_BYTES = 2 * PIECE_BYTES;  // x k-groups then h k-groups of one chunk (kgx = KG for layers >= 1)
+constexpr uint32_t LAYER_BYTES = NCHL * CHUNK_BYTES;   // one CTA's half of a layer
+constexpr uint32_t A_BYTES = KG * ROWS * 16;       // one operand tile (32 KB)
+constexpr uint32_t MASK_BYTES = KG * ROWS * 4;     // keep-bit words of one item
+constexpr int NP = 7;                              // ring depth (slots)
+constexpr int NFULL = 8;                           // "piece landed" barriers, indexed by piece number (> NP: never alias)
+constexpr uint32_t OUT_N = 32;                     // output product: 16 outputs x {fp16(W_o), W_o - fp16(W_o)}
+constexpr uint32_t OUT_BYTES = KG * (OUT_N / 2) * 16;   // this CTA's tile of it (4 KB)
+constexpr uint32_t BAR_BLOCK_BYTES = 512;
+constexpr uint32_t SMEM = A_BYTES + 2 * A_BYTES + 2 * MASK_BYTES + NP * PIECE_BYTES + BAR_BLOCK_BYTES;
+constexpr uint32_t ACC_COLS = 256, HA_COL = 256, HB_COL = 384, H_COLS = H / 2, TMEM_COLS = 512;
+constexpr size_t CSTATE_FLOATS = (size_t)2 * H * ROWS;     // per CTA: [layer][k-group * 2 + half][row] float4
+static_assert(SMEM <= 227 * 1024, "shared memory budget");
+
+enum {
+    BAR_X1_READY = 0, BAR_X1_DONE = 1, BAR_MASK_READY = 2, BAR_ACC_READY = 4, BAR_SLOT_FREE = 6, BAR_HA_READY = 8,
+    BAR_HB_READY = BAR_HA_READY + NCHL, BAR_W_FULL = BAR_HB_READY + NCHL, BAR_W_EMPTY = BAR_W_FULL + NFULL,
+    BAR_OUT_READY = BAR_W_EMPTY + NP, BAR_COUNT = BAR_OUT_READY + 1
+};
+static_assert(BAR_COUNT * 8 + 16 <= BAR_BLOCK_BYTES, "barrier block too small");
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// keep-bit word of 8 units: byte k (k = 0..3) carries unit k in bit 7 and unit 4+k in bit 6.  From the four half2 AND-masks:
+__device__ __forceinline__ uint32_t keep_word(const uint4 m) {
+    return (prmt(m.x, m.y, 0x6420u) & 0x80808080u) | (prmt(m.z, m.w, 0x6420u) & 0x40404040u);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constant__ TcLayerArgs b) {
+    using namespace umma;
+    constexpr uint32_t LBO_A = ROWS * 16, LBO_B = KG_BYTES_B, SBO = 128;
+    const int T = a.T;
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sX1 = smem;                                       // [A_BYTES] layer A's input tile of the current item
+    uint8_t* sX2 = sX1 + A_BYTES;                              // [2][A_BYTES] dropout(h_A) of item i in buffer i & 1
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sX2 + 2 * A_BYTES);   // [2][KG][ROWS] keep-bit words of item i in buffer i & 1
+    uint8_t* sW = reinterpret_cast<uint8_t*>(sMask) + 2 * MASK_BYTES;   // [NP][PIECE_BYTES] weight ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + NP * PIECE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_my_tiles = (a.n_pair_tiles - cluster_id + n_clusters - 1) / n_clusters;
+    const int NI = n_my_tiles * T;                             // items (tile, step) of this pair; waves 0 .. NI
+    const bool has_out = b.preds != nullptr;
+
+    tc::timeline_stamp(a.timeline, 0);
+    if (warp == MMA_WARP) {
+        tmem_alloc<2>(tmem_slot, TMEM_COLS);
+        tmem_relinquish<2>();
+    }
+    if (tid == 0) {
+        mbar_init(&bars[BAR_X1_READY], 2 * LOAD_WARPS);
+        mbar_init(&bars[BAR_X1_DONE], N_ISSUERS);              // each issuer commits after ITS last x-part of layer A
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[BAR_MASK_READY + i], LOAD_WARPS);  // CTA-local
+            mbar_init(&bars[BAR_ACC_READY + i], 1);
+            mbar_init(&bars[BAR_SLOT_FREE + i], 2 * EPI_WARPS);
+        }
+        for (int c = 0; c < NCHL; ++c) {
+            mbar_init(&bars[BAR_HA_READY + c], 2 * EPI_WARPS);
+            mbar_init(&bars[BAR_HB_READY + c], 2 * EPI_WARPS);
+        }
+        for (int p = 0; p < NFULL; ++p) mbar_init(&bars[BAR_W_FULL + p], rank == 0 ? 2 : 1);   // leader: own copy + the peer's forward
+        for (int p = 0; p < NP; ++p) mbar_init(&bars[BAR_W_EMPTY + p], 1);
+        mbar_init(&bars[BAR_OUT_READY], 1);
+        mbar_init_fence();
+    }
+    fence_proxy_async_smem();
+    fence_before_sync();
+    cluster_sync();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    tc::timeline_stamp(a.timeline, 1);
+
+    if (warp < EPI_WARPS) {
+        // =================================== epilogue warps ===========================================================
+        // warp (q, s): rows 32q..32q+31 (its TMEM lane quarter) x the 8 hidden units 8s..8s+7 of EVERY 32-unit chunk of both layers.
+        const int q = warp & 3, s = warp >> 2;
+        const int row_l = 32 * q + lane;
+        const uint32_t t_lane = (uint32_t)(32 * q) << 16;
+        float4* cst0 = reinterpret_cast<float4*>(a.cstate + (size_t)blockIdx.x * CSTATE_FLOATS) + row_l;   // layer A; layer B: + 2 * KG * ROWS
+        uint32_t ph_out = 0;
+        int tA = 0, tB = -1, tileB = cluster_id - n_clusters;  // advanced at the top of every wave
+
+        for (int w = 0; w <= NI; ++w) {
+            const bool A_on = w < NI, B_on = w >= 1;
+            if (w > 0) { if (++tA == T) tA = 0; }
+            if (B_on) { if (++tB == T) tB = 0; if (tB == 0) tileB += n_clusters; }
+            const bool final_out = B_on && has_out && tB == T - 1;
+            const uint32_t bufA = (uint32_t)w & 1u;            // x2 / mask buffer of A's item
+            if (A_on) mbar_wait_wd(&bars[BAR_MASK_READY + bufA], ((uint32_t)w >> 1) & 1u);
+
+            const int hp_begin = A_on ? 0 : 2 * NCHL, hp_end = B_on ? 4 * NCHL : 2 * NCHL;
+            uint32_t rbuf[2][16];
+            float4 cbuf[2];
+            float4 bnext[4];
+            float hlo[4];
+            bool prefetched = true;
+            auto t_of = [&](int layer) { return layer ? tB : tA; };
+            auto request_bias = [&](int hp1) {
+                const float* bs = (hp1 >> 3) ? b.bias_s : a.bias_s;
+                const float4* bias4 = reinterpret_cast<const float4*>(bs + (((hp1 >> 1) & 3) * 32 + 8 * s + 4 * (hp1 & 1)) * 4);
+                bnext[0] = __ldg(bias4); bnext[1] = __ldg(bias4 + 1); bnext[2] = __ldg(bias4 + 2); bnext[3] = __ldg(bias4 + 3);
+            };
+            auto cst_at = [&](int hp1) {                       // this thread's float4 of cell state of half-pass hp1
+                return cst0 + (size_t)((hp1 >> 3) * 2 * KG + (4 * ((hp1 >> 1) & 3) + s) * 2 + (hp1 & 1)) * ROWS;
+            };
+            cbuf[0] = cbuf[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (t_of(hp_begin >> 3) > 0) cbuf[0] = __ldcg(cst_at(hp_begin));
+            request_bias(hp_begin);
+            mbar_wait_wd(&bars[BAR_ACC_READY + 0], 0);          // every group of 4 chunks uses each slot twice: parity = (chunk >> 1) & 1
+            fence_after_sync();
+            tmem_ld_x16(tmem + t_lane + (uint32_t)(32 * s), rbuf[0]);
+#pragma unroll
+            for (int hp = 0; hp < 4 * NCHL; ++hp) {
+                if (hp < hp_begin || hp >= hp_end) continue;
+                const int layer = hp >> 3, cl = (hp >> 1) & 3, half = hp & 1, slot = (hp >> 1) & 1;
+                const int t_cur = t_of(layer);
+                const uint32_t* r = rbuf[hp & 1];
+                const float4 bsv[4] = {bnext[0], bnext[1], bnext[2], bnext[3]};
+                if (half == 0 && hp > hp_begin && !prefetched) {       // the chunk was not complete yet when the last half-pass looked
+                    mbar_wait_wd(&bars[BAR_ACC_READY + slot], (uint32_t)(cl >> 1));
+                    fence_after_sync();
+                    tmem_ld_x16(tmem + t_lane + (uint32_t)(slot * 128 + 32 * s), rbuf[hp & 1]);
+                }
+                tmem_ld_wait();
+                if (half == 1) {                               // chunk fully drained: its issuer may refill the slot
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&bars[BAR_SLOT_FREE + slot], rank);
+                }
+                if (hp + 1 < hp_end) {
+                    const int hp1 = hp + 1, cl1 = (hp1 >> 1) & 3, h1 = hp1 & 1, slot1 = (hp1 >> 1) & 1;
+                    cbuf[hp1 & 1] = t_of(hp1 >> 3) > 0 ? __ldcg(cst_at(hp1)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    prefetched = true;
+                    if (half == 1) {                           // next chunk: prefetch its accumulators only if it is already complete
+                        prefetched = __all_sync(0xffffffffu, mbar_test_wait_addr(smem_u32(&bars[BAR_ACC_READY + slot1]), (uint32_t)(cl1 >> 1)));
+                        if (prefetched) fence_after_sync();
+                    }
+                    if (prefetched) tmem_ld_x16(tmem + t_lane + (uint32_t)(slot1 * 128 + 32 * s + 16 * h1), rbuf[hp1 & 1]);
+                }
+                const int j = 4 * cl + s;                      // k-group of units 32 cl + 8 s .. + 7
+                uint32_t mw = 0;
+                if (layer == 0 && half == 1) mw = sMask[(bufA * KG + (uint32_t)j) * ROWS + row_l];
+
+                // 5 MUFU per cell: sigmoid(x) = 0.5 + 0.5 tanh(x / 2) with the hardware tanh; bias stored as 0.5 b (i, f, o), b (g)
+                float hv[4], cn[4], tg[16];
+                const float cp[4] = {cbuf[hp & 1].x, cbuf[hp & 1].y, cbuf[hp & 1].z, cbuf[hp & 1].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 bs = bsv[u];
+                    tg[4 * u + 0] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 0]), 0.5f, bs.x));
+                    tg[4 * u + 1] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 1]), 0.5f, bs.y));
+                    tg[4 * u + 2] = tanh_approx(__uint_as_float(r[4 * u + 2]) + bs.z);
+                    tg[4 * u + 3] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 3]), 0.5f, bs.w));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float gi = fmaf(tg[4 * u + 0], 0.5f, 0.5f), gf = fmaf(tg[4 * u + 1], 0.5f, 0.5f);
+                    cn[u] = fmaf(gf, cp[u], gi * tg[4 * u + 2]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) hv[u] = fmaf(tg[4 * u + 3], 0.5f, 0.5f) * tanh_approx(cn[u]);
+                if (hp + 1 < hp_end) request_bias(hp + 1);
+                if (t_cur + 1 < T) __stcg(cst_at(hp), make_float4(cn[0], cn[1], cn[2], cn[3]));
+
+                if (half == 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) hlo[u] = hv[u];
+                } else if (layer == 0) {
+                    // h_A(t): fp16 pairs into the TMEM operand buffer of A's next step; dropout(h_A(t)) * 1/(1-p) as fp16 units into
+                    // B's input tile (the scale is applied BEFORE the rounding, as the one-layer kernel does for its out_units)
+                    if (t_cur + 1 < T)
+                        tmem_st_x4(tmem + t_lane + HA_COL + (uint32_t)((t_cur + 1) & 1) * H_COLS + (uint32_t)(4 * j),
+                                   pack_half2(hlo[0], hlo[1]), pack_half2(hlo[2], hlo[3]), pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]));
+                    const float os = a.out_scale;
+                    const uint32_t mw2 = mw << 1;
+                    *reinterpret_cast<uint4*>(sX2 + bufA * A_BYTES + unit_offset(ROWS, row_l, j)) =
+                        make_uint4(pack_half2(hlo[0] * os, hlo[1] * os) & prmt(mw, 0u, 0x9988u), pack_half2(hlo[2] * os, hlo[3] * os) & prmt(mw, 0u, 0xBBAAu),
+                                   pack_half2(hv[0] * os, hv[1] * os) & prmt(mw2, 0u, 0x9988u), pack_half2(hv[2] * os, hv[3] * os) & prmt(mw2, 0u, 0xBBAAu));
+                    if (t_cur + 1 < T) tmem_st_wait();
+                    fence_proxy_async_smem();
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&bars[BAR_HA_READY + cl], rank);
+                } else {
+                    if (t_cur + 1 < T || final_out) {
+                        tmem_st_x4(tmem + t_lane + HB_COL + (uint32_t)((t_cur + 1) & 1) * H_COLS + (uint32_t)(4 * j),
+                                   pack_half2(hlo[0], hlo[1]), pack_half2(hlo[2], hlo[3]), pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]));
+                        tmem_st_wait();
+                    }
+                    if (b.out_units) {
+                        const float os = b.out_scale;
+                        b.out_units[((((size_t)tileB * T + t_cur) * 2 + rank) * KG + j) * ROWS + row_l] =
+                            make_uint4(pack_half2(hlo[0] * os, hlo[1] * os), pack_half2(hlo[2] * os, hlo[3] * os),
+                                       pack_half2(hv[0] * os, hv[1] * os), pack_half2(hv[2] * os, hv[3] * os));
+                    }
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&bars[BAR_HB_READY + cl], rank);
+                }
+            }
+            if (final_out) {                                   // output_layer (nn_models.py:189), last step of the last layer only
+                // Issuer 0 multiplies the published h_T (TMEM) by [fp16(W_o) | W_o - fp16(W_o)]^T (one extra ring piece, N = 32) into
+                // the first 32 columns of B's OTHER h buffer - it held h_{T-1}, which nothing reads any more.
+                mbar_wait_wd(&bars[BAR_OUT_READY], ph_out);
+                ph_out ^= 1;
+                fence_after_sync();
+                uint32_t o32[32];                              // columns 0..15: h_T x fp16(W_o)^T, 16..31: h_T x (W_o - fp16(W_o))^T
+                tmem_ld_x32(tmem + t_lane + HB_COL + (uint32_t)((T & 1) ^ 1) * H_COLS, o32);
+                tmem_ld_wait();
+                const int row = (tileB * 2 + (int)rank) * ROWS + row_l;
+                if (row < b.rows) {
+                    const int e = row / b.n, smp = row - e * b.n;
+                    const int bb = e / b.nF, fb = stream_frame0(b.stream_frames, b.frame0, bb), f = fb + e % b.nF;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {              // this thread: outputs o = s, s+4, ... of its row (O <= 16)
+                        const int o = s + 4 * i;
+                        if (o < b.O && fb >= 0) {              // (an inactive stream keeps its prediction ring untouched)
+                            const float y = __uint_as_float(tc::pick4(o32, i, s)) + __uint_as_float(tc::pick4(o32, 4 + i, s)) + __ldg(b.bo + o);
+                            b.preds[((((size_t)bb * b.pred_ring + f % b.pred_ring) * b.n_out) + smp) * b.O + o] = y;
+                        }
+                    }
+                }
+                fence_before_sync();
+            }
+        }
+    } else if (warp < MMA_WARP) {
+        // =================================== loader warps: x1 of item i, keep-bit words of item i ============================
+        // One thread per row.  Item i's x1 tile may be written once the x-parts of item i-1 have retired (X1_DONE); the loads and
+        // the Philox draws of the first half of the row are done before that wait.
+        const int row_l = tid - EPI_THREADS;
+        constexpr int BK = 8;
+        int t = -1, tile = cluster_id - n_clusters;
+        int e = 0, smp = 0, bidx = 0, f = 0;
+        bool valid = false;
+        for (int i = 0; i < NI; ++i) {
+            if (++t == T) t = 0;
+            if (t == 0) {
+                tile += n_clusters;
+                const int row = (tile * 2 + (int)rank) * ROWS + row_l;
+                valid = row < a.rows;
+                e = valid ? row / a.n : 0; smp = valid ? row - e * a.n : 0;
+                bidx = e / a.nF; f = stream_frame0(a.stream_frames, a.frame0, bidx) + e % a.nF;
+            }
+            const uint32_t stream = a.stream_id0 + (uint32_t)bidx;
+            const uint4* src = reinterpret_cast<const uint4*>(a.in);
+            if (a.in_mode == tc::IN_UNITS) src += ((((size_t)tile * T + t) * 2 + rank) * KG) * ROWS + row_l;
+            else src += ((((size_t)(e >> (a.in_rpc_shift + 1)) * T + t) * 2 + ((e >> a.in_rpc_shift) & 1)) * KG) * ROWS +
+                        (e & ((1 << a.in_rpc_shift) - 1));
+#pragma unroll 1
+            for (int b0 = 0; b0 < KG; b0 += BK) {
+                uint4 pre[BK];
+#pragma unroll
+                for (int jj = 0; jj < BK; ++jj) pre[jj] = valid ? __ldg(src + (size_t)(b0 + jj) * ROWS) : make_uint4(0, 0, 0, 0);
+                if (a.mask_mode == APE_MASK_PHILOX) {
+#pragma unroll
+                    for (int jj = 0; jj < BK; ++jj) {
+                        const uint4 m = APE_PHILOX_DRAW(a, stream, (uint32_t)f, (uint32_t)smp, (uint32_t)a.gap, (uint32_t)t,
+                                                             (uint32_t)(b0 + jj), a.keep_thr16);
+                        pre[jj].x &= m.x; pre[jj].y &= m.y; pre[jj].z &= m.z; pre[jj].w &= m.w;
+                    }
+                } else if (a.mask_mode == APE_MASK_INJECTED && valid) {
+#pragma unroll
+                    for (int jj = 0; jj < BK; ++jj) {
+                        const uint2 m = __ldg(reinterpret_cast<const uint2*>(
+                            a.masks + ((((size_t)e * a.n_gaps + a.gap) * T + t) * a.n + smp) * H + (b0 + jj) * 8));
+                        pre[jj].x &= ((m.x & 0xFFu) ? 0xFFFFu : 0u) | ((m.x & 0xFF00u) ? 0xFFFF0000u : 0u);
+                        pre[jj].y &= ((m.x & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.x & 0xFF000000u) ? 0xFFFF0000u : 0u);
+                        pre[jj].z &= ((m.y & 0xFFu) ? 0xFFFFu : 0u) | ((m.y & 0xFF00u) ? 0xFFFF0000u : 0u);
+                        pre[jj].w &= ((m.y & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.y & 0xFF000000u) ? 0xFFFF0000u : 0u);
+                    }
+                }
+                if (b0 == 0 && i >= 1) mbar_wait_wd(&bars[BAR_X1_DONE], ((uint32_t)(i - 1)) & 1u);
+#pragma unroll
+                for (int jj = 0; jj < BK; ++jj) *reinterpret_cast<uint4*>(sX1 + unit_offset(ROWS, row_l, b0 + jj)) = pre[jj];
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&bars[BAR_X1_READY], rank);
+            // keep-bit words of gap B (between layers A and B) for item i.  Buffer i & 1 was last read by the epilogue during A's
+            // passes of item i-2: those ended before X1_DONE(i-1), which this thread has seen.
+            uint32_t* mdst = sMask + (size_t)((uint32_t)i & 1u) * KG * ROWS + row_l;
+#pragma unroll 4
+            for (int j = 0; j < KG; ++j) {
+                uint32_t wbits = 0xC0C0C0C0u;
+                if (b.mask_mode == APE_MASK_PHILOX) {
+                    wbits = keep_word(APE_PHILOX_DRAW(b, stream, (uint32_t)f, (uint32_t)smp, (uint32_t)b.gap, (uint32_t)t, (uint32_t)j, b.keep_thr16));
+                } else if (b.mask_mode == APE_MASK_INJECTED) {
+                    wbits = 0;
+                    if (valid) {
+                        const uint2 m = __ldg(reinterpret_cast<const uint2*>(
+                            b.masks + ((((size_t)e * b.n_gaps + b.gap) * T + t) * b.n + smp) * H + j * 8));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            wbits |= ((m.x >> (8 * k)) & 0xFFu) ? (0x80u << (8 * k)) : 0u;
+                            wbits |= ((m.y >> (8 * k)) & 0xFFu) ? (0x40u << (8 * k)) : 0u;
+                        }
+                    }
+                }
+                mdst[(size_t)j * ROWS] = wbits;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[BAR_MASK_READY + (i & 1)]);
+        }
+    } else if (warp < TMA_WARP) {
+        if (rank == 0) {
+            // =============================== MMA issuers (leader CTA; the whole warp runs, one elected lane issues) =====
+            // Issuer k owns accumulator slot k, i.e. chunks 1, 3 (k = 1) or 0, 2 (k = 0) of every layer group.  Both walk the whole
+            // piece sequence (ring position and piece number advance with every piece) and act on their own chunks only.
+            const uint32_t my_slot = (uint32_t)(warp - MMA_WARP);
+            const uint32_t idesc = make_idesc_f16(256, 128), idesc_out = make_idesc_f16(256, OUT_N);
+            const uint64_t dX1 = make_desc(smem_u32(sX1), LBO_A, SBO), dX2 = make_desc(smem_u32(sX2), LBO_A, SBO);
+            const uint64_t dW = make_desc(smem_u32(sW), LBO_B, SBO);
+            const uint32_t bar_full = smem_u32(&bars[BAR_W_FULL]), bar_empty = smem_u32(&bars[BAR_W_EMPTY]);
+            const uint32_t d_tmem = tmem + my_slot * 128u;
+            uint32_t wslot = 0, gpiece = 0, uses = 0;
+            auto ring_next = [&]() { wslot = wslot + 1 == NP ? 0 : wslot + 1; ++gpiece; };
+            auto wait_full = [&]() {
+                uint32_t spins = 0;
+                while (!mbar_try_wait_addr(bar_full + (gpiece & (NFULL - 1)) * 8, (gpiece / NFULL) & 1)) { if (++spins > MBAR_WD_SPINS) __trap(); }
+            };
+            // one chunk of one layer: x-part from the shared-memory tile `dx`, recurrent part (t > 0) from the TMEM buffer `h_tmem`
+            auto chunk = [&](int cl, bool mine, int t, uint64_t dx, uint32_t h_tmem, bool x1_layer) {
+                if (!mine) { ring_next(); if (t > 0) ring_next(); return; }
+                if (uses >= 1) mbar_wait_wd(&bars[BAR_SLOT_FREE + my_slot], (uses & 1) ^ 1);   // the epilogue drained the previous occupant
+                ++uses;
+                wait_full();
+                fence_after_sync();
+                if (elect_one()) {
+                    const uint64_t bd = dW + wslot * (PIECE_BYTES >> 4);
+                    mma_f16<2>(d_tmem, dx, bd, idesc, 0u);
+#pragma unroll
+                    for (uint32_t m = 1; m < KG / 2; ++m) mma_f16<2>(d_tmem, dx + m * (2 * LBO_A >> 4), bd + m * (2 * LBO_B >> 4), idesc, 1u);
+                    commit_pair_addr(bar_empty + wslot * 8, 0x3);          // both CTAs' producers may refill this slot
+                    if (t == 0) commit_pair(&bars[BAR_ACC_READY + my_slot], 0x3);
+                    if (x1_layer && cl >= NCHL - 2) commit_pair(&bars[BAR_X1_DONE], 0x3);
+                }
+                __syncwarp();
+                ring_next();
+                if (t > 0) {
+                    wait_full();
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint64_t bd = dW + wslot * (PIECE_BYTES >> 4);
+#pragma unroll
+                        for (uint32_t m = 0; m < KG / 2; ++m) mma_f16_ts<2>(d_tmem, h_tmem + 8 * m, bd + m * (2 * LBO_B >> 4), idesc, 1u);
+                        commit_pair_addr(bar_empty + wslot * 8, 0x3);
+                        commit_pair(&bars[BAR_ACC_READY + my_slot], 0x3);
+                    }
+                    __syncwarp();
+                    ring_next();
+                }
+            };
+            // output layer of a finished tile: h_T (TMEM, B's buffer T & 1) x [fp16(W_o) | W_o - fp16(W_o)]^T into B's other h buffer
+            auto out_piece = [&](uint32_t item_parity) {
+                if (my_slot == 0) {
+                    mbar_wait_wd(&bars[BAR_HB_READY + NCHL - 1], item_parity);     // all of h_T (slices are published in order)
+                    wait_full();
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint64_t bd = make_desc(smem_u32(sW) + wslot * PIECE_BYTES, (OUT_N / 2) * 16, SBO);
+                        const uint32_t at = tmem + HB_COL + (uint32_t)(T & 1) * H_COLS, dt = tmem + HB_COL + (uint32_t)((T & 1) ^ 1) * H_COLS;
+#pragma unroll
+                        for (uint32_t m = 0; m < KG / 2; ++m) mma_f16_ts<2>(dt, at + 8 * m, bd + m * (2 * (OUT_N / 2) * 16 >> 4), idesc_out, m > 0 ? 1u : 0u);
+                        commit_pair_addr(bar_empty + wslot * 8, 0x3);
+                        commit_pair(&bars[BAR_OUT_READY], 0x3);
+                    }
+                    __syncwarp();
+                }
+                ring_next();
+            };
+            int tA = 0, tB = -1;
+            for (int w = 0; w <= NI; ++w) {
+                const bool A_on = w < NI, B_on = w >= 1;
+                if (w > 0) { if (++tA == T) tA = 0; }
+                if (B_on) { if (++tB == T) tB = 0; }
+                // h_A of item w-1 (A's recurrent operand, and B's input x2 of item w-1) is complete.  Waited for here, at the top of the
+                // wave, by both issuers: the barrier cannot run a second phase ahead, because item w's chunks are issued below.
+                if (w >= 1) mbar_wait_wd(&bars[BAR_HA_READY + NCHL - 1], ((uint32_t)(w - 1)) & 1u);
+                if (A_on) {
+                    mbar_wait_wd(&bars[BAR_X1_READY], (uint32_t)w & 1u);
+                    fence_after_sync();
+                    const uint32_t hA = tmem + HA_COL + (uint32_t)(tA & 1) * H_COLS;
+#pragma unroll
+                    for (int cl = 0; cl < NCHL; ++cl) {
+                        if (cl == 2 && has_out && w >= 2 && tB == 0) out_piece(((uint32_t)(w - 2)) & 1u);   // the previous tile's output layer
+                        chunk(cl, (uint32_t)(cl & 1) == my_slot, tA, dX1, hA, true);
+                    }
+                }
+                if (B_on) {
+                    if (w >= 2) mbar_wait_wd(&bars[BAR_HB_READY + NCHL - 1], ((uint32_t)(w - 2)) & 1u);   // h_B of item w-2
+                    fence_after_sync();
+                    const uint64_t dx = dX2 + (((uint32_t)(w - 1)) & 1u) * (A_BYTES >> 4);
+                    const uint32_t hB = tmem + HB_COL + (uint32_t)(tB & 1) * H_COLS;
+#pragma unroll
+                    for (int cl = 0; cl < NCHL; ++cl) chunk(cl, (uint32_t)(cl & 1) == my_slot, tB, dx, hB, false);
+                }
+            }
+            if (has_out) out_piece(((uint32_t)(NI - 1)) & 1u);   // the last tile's output layer
+        } else if (warp == MMA_WARP && lane == 0) {
+            // =============================== peer CTA: forward "piece landed in my ring" to the leader ==================
+            uint32_t gpiece = 0;
+            auto forward = [&]() {
+                mbar_wait_wd(&bars[BAR_W_FULL + (gpiece & (NFULL - 1))], (gpiece / NFULL) & 1);
+                mbar_arrive_remote(&bars[BAR_W_FULL + (gpiece & (NFULL - 1))], 0);
+                ++gpiece;
+            };
+            int tA = 0, tB = -1;
+            for (int w = 0; w <= NI; ++w) {
+                const bool A_on = w < NI, B_on = w >= 1;
+                if (w > 0) { if (++tA == T) tA = 0; }
+                if (B_on) { if (++tB == T) tB = 0; }
+                if (A_on) for (int cl = 0; cl < NCHL; ++cl) {
+                    if (cl == 2 && has_out && w >= 2 && tB == 0) forward();
+                    forward();
+                    if (tA > 0) forward();
+                }
+                if (B_on) for (int cl = 0; cl < NCHL; ++cl) { forward(); if (tB > 0) forward(); }
+            }
+            if (has_out) forward();
+        }
+    } else if (lane == 0) {
+        // =================================== weight-ring producer (one lane per CTA) =====================================
+        const uint8_t* WA = a.W + (size_t)rank * LAYER_BYTES;  // this CTA's half of each layer's weight tiles
+        const uint8_t* WB = b.W + (size_t)rank * LAYER_BYTES;
+        uint32_t wslot = 0, wphase = 0, gpiece = 0;
+        bool wrapped = false;
+        auto put = [&](const uint8_t* src, uint32_t bytes) {
+            uint64_t* full = &bars[BAR_W_FULL + (gpiece & (NFULL - 1))];
+            if (wrapped) mbar_wait_wd(&bars[BAR_W_EMPTY + wslot], wphase ^ 1);   // previous occupant consumed
+            mbar_arrive_expect_tx(full, bytes);
+            bulk_g2s(sW + wslot * PIECE_BYTES, src, bytes, full);
+            if (++wslot == NP) { wslot = 0; wphase ^= 1; wrapped = true; }
+            ++gpiece;
+        };
+        int tA = 0, tB = -1;
+        for (int w = 0; w <= NI; ++w) {
+            const bool A_on = w < NI, B_on = w >= 1;
+            if (w > 0) { if (++tA == T) tA = 0; }
+            if (B_on) { if (++tB == T) tB = 0; }
+            if (A_on) for (int cl = 0; cl < NCHL; ++cl) {
+                if (cl == 2 && has_out && w >= 2 && tB == 0) put(b.Wo16 + (size_t)rank * OUT_BYTES, OUT_BYTES);
+                put(WA + (size_t)cl * CHUNK_BYTES, PIECE_BYTES);
+                if (tA > 0) put(WA + (size_t)cl * CHUNK_BYTES + PIECE_BYTES, PIECE_BYTES);
+            }
+            if (B_on) for (int cl = 0; cl < NCHL; ++cl) {
+                put(WB + (size_t)cl * CHUNK_BYTES, PIECE_BYTES);
+                if (tB > 0) put(WB + (size_t)cl * CHUNK_BYTES + PIECE_BYTES, PIECE_BYTES);
+            }
+        }
+        if (has_out) put(b.Wo16 + (size_t)rank * OUT_BYTES, OUT_BYTES);
+    }
+    __syncwarp();
+    fence_before_sync();
+    cluster_sync();
+    tc::timeline_stamp(a.timeline, 2);
+    if (warp == MMA_WARP) tmem_dealloc<2>(tmem, TMEM_COLS);
+}
+
+bool supported(int Hh, int T, int O) { return Hh == H && T >= 2 && O <= (int)OUT_N / 2; }
+
+size_t scratch_bytes(int Hh, int sm_count) { return Hh == H ? (size_t)sm_count * CSTATE_FLOATS * sizeof(float) : 0; }
+
+// layers A = a, B = b of one launch; a.cstate: scratch_bytes() bytes
+int launch_pair(const TcLayerArgs& a, const TcLayerArgs& b, int sm_count, cudaStream_t st) {
+    if (a.kgx != KG || b.kgx != KG || a.rpc != ROWS || !a.cstate || a.T != b.T || a.T < 2) return APE_ERR_UNSUPPORTED;
+    if (a.in_mode != tc::IN_UNITS && a.in_mode != tc::IN_SHARED_UNITS) return APE_ERR_UNSUPPORTED;
+    if (b.preds && (!b.Wo16 || b.O > (int)OUT_N / 2)) return APE_ERR_UNSUPPORTED;
+    APE_CUDA_TRY(cudaFuncSetAttribute(lstm_pair_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    int clusters = sm_count / 2;
+    if (clusters > a.n_pair_tiles) clusters = a.n_pair_tiles;
+    lstm_pair_tcw_kernel<<<2 * clusters, THREADS, SMEM, st>>>(a, b);
+    return check_launch();
+}
+
+}  // namespace tcw
+}  // namespace ape

@@ -3,7 +3,8 @@
 Same keys and float positions as ``WATCH_ONLY_IMU_LOOKUP`` (28 floats,
 ``src/wear_mocap_ape/data_types/messaging.py:20-68``) and ``WATCH_PHONE_IMU_LOOKUP`` (55 floats,
 ``messaging.py:96-187``) of the reference; built here from per-device field groups.  The CUDA feature
-kernel addresses the same positions (``csrc/ape_layouts.cuh``); ``tests/test_tables.py`` pins both.
+kernel addresses the same positions (``csrc/ape_features.cuh``); ``tests/test_oracle_golden.py`` pins the tables
+against ``tests/golden/tables.json`` (exported from the reference).
 """
 
 

@@ -12,6 +12,7 @@ of the stream axis (``shard_streams``) with no collective.
 from dataclasses import dataclass
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -105,7 +106,7 @@ class BatchedEstimator:
     def __init__(self, kind, layout, state, seq_len, y_targets, stats, n_streams, mc_samples,
                  smooth=1, dropout=0.2, bonemap=None, frames_per_call=1, emit_samples=True, normalize=True,
                  mask_mode=N.MASK_PHILOX, philox_seed=0, first_stream=0, device=None,
-                 lstm_variant="auto", tc_min_rows=1, tc_tolerance_m=5e-5, pipeline=True, lanes=True):
+                 lstm_variant="auto", tc_min_rows=1, tc_tolerance_m=5e-5, pipeline=True, lanes=True, tc_flags=None):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedEstimator needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = N.load()
@@ -124,6 +125,9 @@ class BatchedEstimator:
         self.mask_mode, self.philox_seed, self.first_stream = int(mask_mode), int(philox_seed), int(first_stream)
         self.emit_samples = bool(emit_samples)
         self.normalize = bool(normalize)
+        # tensor-core path, H = 128, L >= 3: 0 = pairs of layers >= 1 as one wavefront launch when the batch fills the GPU,
+        # 1 = always one launch per layer, 2 = always wavefront pairs (include/ape_b200.h: ape_lstm_args.tc_flags)
+        self.tc_flags = int(os.environ.get("APE_TC_FLAGS", "0")) if tc_flags is None else int(tc_flags)     # (the variable: A/B runs of bench.py)
         self.ncols = LAYOUT_NCOLS[self.layout]
         dev, f32 = self.device, torch.float32
         with torch.cuda.device(dev):
@@ -133,6 +137,7 @@ class BatchedEstimator:
                 self.xx_s = torch.as_tensor(np.asarray(stats["xx_s"], dtype=np.float64)).to(dev)
                 self.yy_m = torch.as_tensor(np.asarray(stats["yy_m"], dtype=np.float32)).to(dev)
                 self.yy_s = torch.as_tensor(np.asarray(stats["yy_s"], dtype=np.float32)).to(dev)
+                self.yy_m_host, self.yy_s_host = np.asarray(stats["yy_m"], dtype=np.float64), np.asarray(stats["yy_s"], dtype=np.float64)
             else:
                 self.xx_m = self.xx_s = self.yy_m = self.yy_s = None
             self.body = torch.as_tensor(body_measurements_row(bonemap).astype(np.float32).ravel()).to(dev)
@@ -206,6 +211,15 @@ class BatchedEstimator:
     def _lstm_fn(self, variant=None):
         return self.lib.ape_mc_lstm_tc if (variant or self.lstm_variant) == "tc" else self.lib.ape_mc_lstm_fma
 
+    def _lstm_launches(self, a):
+        """Kernels the LSTM stage launches for the argument block ``a`` (pairs of layers of an H = 128 model count once)."""
+        if self.lstm_variant != "tc":
+            return self.L
+        a.layer_begin = a.layer_end = 0
+        n = ctypes.c_int(0)
+        N.check(self.lib.ape_mc_lstm_tc_launch_count(a, ctypes.byref(n)), "ape_mc_lstm_tc_launch_count")
+        return n.value
+
     def _probe_tc_error(self, n_est=16, n_samples=64):
         """Max |position| difference (metres) between the tensor-core and the fp32 LSTM kernels on a probe batch:
         N(0,1) normalised windows, the same Philox masks for both (the keying does not depend on the kernel)."""
@@ -251,29 +265,15 @@ class BatchedEstimator:
         self.frame = 0
 
     # ---- device path -----------------------------------------------------------------------------------
-    def step_device(self, raw, n_frames=None, masks=None, layer_ms=None, trace=None, trace_layer=1, raw_ready=False,
-                    _h2d_from=None, stream_frames=None, _frames_from=None, _out_slot=None, timeline=None, _plain=False):
-        """``raw``: device tensor ``[B, nF, ncols]`` float32 (nF <= frames_per_call).  Enqueues the three stages and returns an
-        ``EstimateBatch`` of views into the estimator's device buffers (valid until the call after next).  ``raw_ready=True``
-        promises that ``raw`` is already materialised (not pending on the current stream), which lets the pipelined path
-        start stage 1 + layer 0 of this call under the previous call's kernels.  ``stream_frames``: optional device int32
-        tensor ``[B]`` of per-stream absolute frame numbers for streams that do not advance in lock-step (a negative entry
-        skips the stream in this call: its rings and outputs stay untouched); the shared frame counter is then not used."""
-        nF = int(raw.shape[1]) if n_frames is None else int(n_frames)
-        if raw.shape[0] != self.B or nF > self.nF_max or raw.shape[2] != self.ncols or not raw.is_contiguous():
-            raise UserWarning(f"raw rows must be a contiguous [B={self.B}, nF<={self.nF_max}, {self.ncols}] tensor, got {tuple(raw.shape)}")
-        if raw.dtype != torch.float32:
-            raise UserWarning("raw rows must be float32 (the wire format, messaging.py)")
-        lib, B = self.lib, self.B
-        main = torch.cuda.current_stream()
+    def _lstm_args(self, nF, frame0, sf, masks):
+        """The stage-2 argument block of one call over the feature ring (and the device copy of injected masks, kept alive
+        by the caller until the launch is enqueued)."""
+        B = self.B
         a = N.LstmArgs()
         a.weights = self.weights.data_ptr()
         a.I, a.H, a.L, a.T, a.O = self.I, self.H, self.L, self.T, self.O
         a.dropout_p = self.p
         a.x_dense, a.feat_ring_buf, a.feat_ring = None, self.feats.data_ptr(), self.feat_ring
-        frame0, sf = (self.frame, None) if stream_frames is None else (0, stream_frames)
-        if sf is not None and (sf.dtype != torch.int32 or sf.numel() != B or not sf.is_cuda):
-            raise UserWarning("stream_frames must be a device int32 tensor of B entries")
         a.B, a.nF, a.frame0, a.n_samples = B, nF, frame0, self.n
         a.stream_frames = None if sf is None else sf.data_ptr()
         a.mask_mode = self.mask_mode if self.L > 1 else N.MASK_NONE
@@ -289,6 +289,57 @@ class BatchedEstimator:
         a.workspace = self.workspace.data_ptr()
         a.preds, a.pred_ring, a.all_steps = self.preds.data_ptr(), self.pred_ring, 0
         a.weights_tc = None if self.tc_weights is None else self.tc_weights.data_ptr()
+        # the workspace is laid out for the largest call, so short calls in flight beside full ones agree on every offset
+        a.ws_E, a.tc_flags = B * self.nF_max, self.tc_flags
+        return a, md
+
+    # ---- the reference's three per-frame calls, one by one (estimator.py:174-176) ------------------------------------
+    def step_features(self, xx, masks=None):
+        """``add_xx_to_row_hist_and_make_prediction`` for all streams: ``xx [B, I]`` float64 rows as ``parse_row_to_xx`` returned
+        them -> z-score -> feature ring -> MC-dropout LSTM -> prediction ring; returns the de-normalised predictions of the
+        smoothing window ``[B, smooth * n, O]`` (oldest frame first, frames before 0 read as frame 0: the reference's
+        ``_row_hist`` / ``_smooth_hist`` lists are the two device rings).  Advances the frame counter."""
+        xx = np.ascontiguousarray(xx, dtype=np.float64).reshape(self.B, self.I)
+        with torch.cuda.device(self.device):
+            st = N.current_stream_ptr()
+            xd = torch.from_numpy(xx).to(self.device)
+            N.check(self.lib.ape_features_push(N.ptr(xd), self.I, N.ptr(self.xx_m), N.ptr(self.xx_s), 1 if self.normalize else 0,
+                                               N.ptr(self.feats), self.B, self.frame, None, self.feat_ring, st), "ape_features_push")
+            a, md = self._lstm_args(1, self.frame, None, masks)
+            N.check(self._lstm_fn()(a, st), "ape_mc_lstm")
+            slots = [max(0, k) % self.pred_ring for k in range(self.frame - self.smooth + 1, self.frame + 1)]
+            window = self.preds[:, slots].cpu().numpy().astype(np.float64)          # [B, smooth, n, O]
+        if self.normalize:
+            window = window * self.yy_s_host + self.yy_m_host                       # estimator.py:108-109
+        self.launches += 1 + self._lstm_launches(a)
+        self.calls += 1
+        self.frame += 1
+        return window.reshape(self.B, self.S, self.O)
+
+    def step_device(self, raw, *args, **kwargs):
+        """See ``_step_device``; runs it with the estimator's device current (kernels, streams and events all belong to it)."""
+        with torch.cuda.device(self.device):
+            return self._step_device(raw, *args, **kwargs)
+
+    def _step_device(self, raw, n_frames=None, masks=None, layer_ms=None, trace=None, trace_layer=1, raw_ready=False,
+                     _h2d_from=None, stream_frames=None, _frames_from=None, _out_slot=None, timeline=None, _plain=False):
+        """``raw``: device tensor ``[B, nF, ncols]`` float32 (nF <= frames_per_call).  Enqueues the three stages and returns an
+        ``EstimateBatch`` of views into the estimator's device buffers (valid until the call after next).  ``raw_ready=True``
+        promises that ``raw`` is already materialised (not pending on the current stream), which lets the pipelined path
+        start stage 1 + layer 0 of this call under the previous call's kernels.  ``stream_frames``: optional device int32
+        tensor ``[B]`` of per-stream absolute frame numbers for streams that do not advance in lock-step (a negative entry
+        skips the stream in this call: its rings and outputs stay untouched); the shared frame counter is then not used."""
+        nF = int(raw.shape[1]) if n_frames is None else int(n_frames)
+        if raw.shape[0] != self.B or nF > self.nF_max or raw.shape[2] != self.ncols or not raw.is_contiguous():
+            raise UserWarning(f"raw rows must be a contiguous [B={self.B}, nF<={self.nF_max}, {self.ncols}] tensor, got {tuple(raw.shape)}")
+        if raw.dtype != torch.float32:
+            raise UserWarning("raw rows must be float32 (the wire format, messaging.py)")
+        lib, B = self.lib, self.B
+        main = torch.cuda.current_stream()
+        frame0, sf = (self.frame, None) if stream_frames is None else (0, stream_frames)
+        if sf is not None and (sf.dtype != torch.int32 or sf.numel() != B or not sf.is_cuda):
+            raise UserWarning("stream_frames must be a device int32 tensor of B entries")
+        a, md = self._lstm_args(nF, frame0, sf, masks)
         if layer_ms is not None:                     # profiling leg: float32 host array of L entries, filled on return
             a.layer_ms = layer_ms.ctypes.data
         if trace is not None:                        # debugging: device int64[768] of SM-clock stamps (tensor-core path)
@@ -366,7 +417,7 @@ class BatchedEstimator:
             features(st)
             N.check(self._lstm_fn()(a, st), "ape_mc_lstm")
             stage3(st)
-        self.launches += 2 + self.L
+        self.launches += 2 + self._lstm_launches(a)
         self.calls += 1
         out = EstimateBatch(self._view(self.msg, nF), self._view(self.std, nF), self._view(self.samples, nF),
                             self._view(self.status, nF), self.frame)
@@ -463,7 +514,7 @@ class BatchedEstimator:
         out = EstimateBatch(msg, std, samples, status, self.frame)
         self.frame += nF
         self.calls += 1
-        self.launches += 2 + self.L
+        self.launches += 2 + self._graph_lstm_launches
         return out
 
     def _capture_graph(self, nF):
@@ -494,6 +545,7 @@ class BatchedEstimator:
         with torch.cuda.graph(self._graph, stream=side):
             enqueue()
         self._graph_nF = nF
+        self._graph_lstm_launches = (self.launches - saved[2]) // 2 - 2      # (the eager pass and the capture each counted one call)
         self.frame, self.calls, self.launches = saved
 
     def _host_views(self, slot, nF):

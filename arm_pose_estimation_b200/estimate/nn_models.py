@@ -122,20 +122,34 @@ def _require_cuda():
 
 
 class DropoutLSTM:
+    """The reference's ``DropoutLSTM`` module surface (nn_models.py:160-207) over the CUDA path.
+
+    ``lstm_variant``: ``"fp32"`` = the exact FFMA kernel, ``"tc"`` = the tcgen05 tensor-core kernels (fp16 operands, fp32
+    accumulation and state), ``"auto"`` (default) = tensor cores when this model's shape is supported AND a probe on its own
+    weights keeps the tensor-core outputs within ``tc_tolerance`` (normalised output units; 2e-4 is ~3e-5 m of hand position)
+    of the fp32 kernel's.  A caller-supplied ``hs`` always takes the fp32 kernel."""
+
     def __init__(self, input_size, hidden_layer_size, hidden_layer_count, output_size, dropout=0.2,
-                 philox_seed=None, precision="fp32"):
+                 philox_seed=None, precision="fp32", lstm_variant="auto", tc_tolerance=2e-4):
         self.output_size = int(output_size)
         self.input_size = int(input_size)
         self.hidden_layer_size = int(hidden_layer_size)
         self.hidden_layer_count = int(hidden_layer_count)
         self.dropout = float(dropout)
         self.precision = precision
+        if lstm_variant not in ("auto", "fp32", "tc"):
+            raise UserWarning(f"lstm_variant must be 'auto', 'fp32' or 'tc', got {lstm_variant!r}")
+        self.lstm_variant = lstm_variant
+        self.tc_tolerance = float(tc_tolerance)
+        self.tc_probe_error = None           # max |tc - fp32| over the probe batch, once measured
         self.lstm = _LstmMode()
         self.philox_seed = int(torch.initial_seed() if philox_seed is None else philox_seed) & (2 ** 64 - 1)
         self._calls = 0                      # Philox "frame" counter: fresh masks on every call
         self._state = None
         self._blob = None                    # device copy of the packed weights (built lazily)
+        self._blob_tc = None
         self._ws = None
+        self._tc_ok = None                   # outcome of the probe (None: not run yet)
 
     # ---- torch.nn.Module-like surface ---------------------------------------------------------------
     def load_state_dict(self, state):
@@ -145,7 +159,7 @@ class DropoutLSTM:
                                f"{(self.input_size, self.hidden_layer_size, self.hidden_layer_count, self.output_size)}")
         self._state = {k: torch.as_tensor(np.asarray(v.detach().cpu() if isinstance(v, torch.Tensor) else v,
                                                      dtype=np.float32)) for k, v in state.items()}
-        self._blob = None
+        self._blob = self._blob_tc = self._tc_ok = None
         return self
 
     def state_dict(self):
@@ -168,14 +182,89 @@ class DropoutLSTM:
             self._blob = torch.from_numpy(pack_lstm_weights(self._state)).cuda()
         return self._blob
 
-    def _workspace(self, T, E, n):
-        need = N.workspace_bytes(self.input_size, self.hidden_layer_size, self.hidden_layer_count, T,
-                                 self.output_size, E, n)
+    def packed_weights_tc(self):
+        """Device tensor holding the fp16 blob of the tensor-core kernels."""
+        self.packed_weights()
+        if self._blob_tc is None:
+            self._blob_tc = torch.from_numpy(pack_lstm_weights_tc(self._state)).cuda()
+        return self._blob_tc
+
+    def _dims(self):
+        return self.input_size, self.hidden_layer_size, self.hidden_layer_count, self.output_size
+
+    def _workspace(self, T, E, n, tc):
+        I, H, L, O = self._dims()
+        need = N.workspace_bytes(I, H, L, T, O, E, n, tensor_core=tc, all_steps=tc)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
         return self._ws
 
-    def _run(self, x, n_samples, mask_mode, masks=None):
+    def _tc_supported(self, T):
+        I, H, L, O = self._dims()
+        return N.tc_supported(I, H, L, O) and T <= 40
+
+    def _use_tc(self, T):
+        """Which kernel a call without ``hs`` takes (see the class docstring)."""
+        if self.lstm_variant == "fp32":
+            return False
+        if not self._tc_supported(T):
+            if self.lstm_variant == "tc":
+                raise UserWarning(f"the tensor-core LSTM kernels do not take (I,H,L,O)={self._dims()} with T={T}")
+            return False
+        if self.lstm_variant == "tc":
+            return True
+        if self._tc_ok is None:                  # probe: N(0,1) windows, dropout active, the same Philox masks through both kernels
+            g = torch.Generator(device="cpu").manual_seed(1234)
+            x = torch.randn((8, T, self.input_size), generator=g, dtype=torch.float32).cuda()
+            calls = self._calls
+            outs = []
+            for tc in (False, True):
+                self._calls = 0x5EED
+                outs.append(self._launch(x, 16, N.MASK_PHILOX, None, None, tc))
+            self._calls = calls
+            self.tc_probe_error = float((outs[0] - outs[1]).abs().max().item())
+            self._tc_ok = self.tc_probe_error <= self.tc_tolerance
+        return self._tc_ok
+
+    def _launch(self, xd, n_kernel, mask_mode, md, hs, tc):
+        """One call of the C ABI: ``xd [E, T, I]`` on the device -> ``[E, n_kernel, T, O]``."""
+        I, H, L, O = self._dims()
+        E, T, _ = xd.shape
+        preds = torch.empty((E, n_kernel, T, O), dtype=torch.float32, device="cuda")
+        a = N.LstmArgs()
+        a.weights = self.packed_weights().data_ptr()
+        a.weights_tc = self.packed_weights_tc().data_ptr() if tc else None
+        a.I, a.H, a.L, a.T, a.O = I, H, L, T, O
+        a.dropout_p = self.dropout
+        a.x_dense, a.feat_ring_buf, a.feat_ring = xd.data_ptr(), None, 0
+        a.B, a.nF, a.frame0 = E, 1, self._calls & 0x7FFFFFFF
+        a.n_samples = n_kernel
+        a.mask_mode = mask_mode
+        if md is not None:
+            a.masks = md.data_ptr()
+        if hs is not None:
+            a.h0, a.c0 = hs[0].data_ptr(), hs[1].data_ptr()
+        a.philox_seed, a.stream_id0 = self.philox_seed, 0
+        a.workspace = self._workspace(T, E, n_kernel, tc).data_ptr()
+        a.preds, a.pred_ring, a.all_steps = preds.data_ptr(), 1, 1
+        fn, what = (N.load().ape_mc_lstm_tc, "ape_mc_lstm_tc") if tc else (N.load().ape_mc_lstm_fma, "ape_mc_lstm_fma")
+        N.check(fn(a, N.current_stream_ptr()), what)
+        return preds
+
+    def _initial_state(self, hs, rows):
+        """``hs = (h_0, c_0)``, each ``[L, rows, H]`` like torch.nn.LSTM takes them -> contiguous float32 device tensors."""
+        L, H = self.hidden_layer_count, self.hidden_layer_size
+        if not isinstance(hs, (tuple, list)) or len(hs) != 2:
+            raise UserWarning("hs must be the pair (h_0, c_0)")
+        out = []
+        for name, v in zip(("h_0", "c_0"), hs):
+            v = torch.as_tensor(v).detach().to(device="cuda", dtype=torch.float32).contiguous()
+            if tuple(v.shape) != (L, rows, H):
+                raise UserWarning(f"{name} must be [{L}, {rows}, {H}] (layers, batch, hidden), got {tuple(v.shape)}")
+            out.append(v)
+        return out
+
+    def _run(self, x, n_samples, mask_mode, masks=None, hs=None):
         _require_cuda()
         if x.dim() != 3 or x.shape[2] != self.input_size:
             raise UserWarning(f"expected x of shape [batch, sequence, {self.input_size}], got {tuple(x.shape)}")
@@ -184,27 +273,25 @@ class DropoutLSTM:
         E, T, _ = xd.shape
         L, H, O = self.hidden_layer_count, self.hidden_layer_size, self.output_size
         n_kernel = 1 if L == 1 else n_samples            # no dropout in a single-layer model: samples are identical
-        preds = torch.empty((E, n_kernel, T, O), dtype=torch.float32, device="cuda")
-        a = N.LstmArgs()
-        a.weights = self.packed_weights().data_ptr()
-        a.I, a.H, a.L, a.T, a.O = self.input_size, H, L, T, O
-        a.dropout_p = self.dropout
-        a.x_dense, a.feat_ring_buf, a.feat_ring = xd.data_ptr(), None, 0
-        a.B, a.nF, a.frame0 = E, 1, self._calls & 0x7FFFFFFF
-        a.n_samples = n_kernel
-        a.mask_mode = mask_mode
         md = None
         if mask_mode == N.MASK_INJECTED and L > 1:
             md = torch.as_tensor(np.asarray(masks) if not isinstance(masks, torch.Tensor) else masks)
             md = md.to(device="cuda", dtype=torch.uint8).contiguous()
             if md.numel() != E * (L - 1) * T * n_kernel * H:
                 raise UserWarning(f"masks must hold E*(L-1)*T*n*H = {E * (L - 1) * T * n_kernel * H} entries, got {md.numel()}")
-            a.masks = md.data_ptr()
-        a.philox_seed, a.stream_id0 = self.philox_seed, 0
-        ws = self._workspace(T, E, n_kernel)
-        a.workspace = ws.data_ptr()
-        a.preds, a.pred_ring, a.all_steps = preds.data_ptr(), 1, 1
-        N.check(N.load().ape_mc_lstm_fma(a, N.current_stream_ptr()), "ape_mc_lstm_fma")
+        if hs is not None:
+            # torch.nn.LSTM(x, hs) with a per-row state (nn_models.py:180-207; batch = n_samples in the MC call): every MC sample
+            # becomes an estimate of its own, so layer 0 runs per row too - it no longer sees the same state for all samples
+            rows = E * n_samples
+            state = self._initial_state(hs, rows)
+            if n_samples > 1:
+                xd = xd.repeat_interleave(n_samples, dim=0)
+                if md is not None:                       # [E][L-1][T][n][H] -> [E * n][L-1][T][1][H]
+                    md = md.view(E, L - 1, T, n_samples, H).permute(0, 3, 1, 2, 4).contiguous()
+            out = self._launch(xd, 1, mask_mode, md, state, False).reshape(rows, T, O)
+            self._calls += 1
+            return out.cpu() if host_in else out
+        preds = self._launch(xd, n_kernel, mask_mode, md, None, self._use_tc(T))
         self._calls += 1
         out = preds.reshape(E * n_kernel, T, O)
         if n_kernel != n_samples:
@@ -212,23 +299,19 @@ class DropoutLSTM:
         return out.cpu() if host_in else out
 
     def forward(self, x, hs=None):
-        """``x [batch, sequence, input] -> [batch, sequence, output]`` (nn_models.py:180-189)."""
-        if hs is not None:
-            raise UserWarning("a caller-supplied initial (h_0, c_0) is not supported: the estimators always start from zeros")
-        return self._run(x, 1, N.MASK_PHILOX if self.lstm.training else N.MASK_NONE)
+        """``x [batch, sequence, input] -> [batch, sequence, output]`` (nn_models.py:180-189); ``hs``: optional ``(h_0, c_0)``,
+        each ``[layers, batch, hidden]``."""
+        return self._run(x, 1, N.MASK_PHILOX if self.lstm.training else N.MASK_NONE, hs=hs)
 
     __call__ = forward
 
     def monte_carlo_predictions(self, n_samples, x, hs=None, masks=None):
-        """``x [1, sequence, input] -> [n_samples, sequence, output]`` with dropout active (nn_models.py:191-207)."""
+        """``x [1, sequence, input] -> [n_samples, sequence, output]`` with dropout active (nn_models.py:191-207); ``hs``:
+        optional ``(h_0, c_0)``, each ``[layers, n_samples, hidden]`` (the batch the reference's LSTM sees is the repeated input)."""
         if x.shape[0] > 1:
             raise UserWarning("MC predictions only for batch size 1")
-        if hs is not None:
-            raise UserWarning("a caller-supplied initial (h_0, c_0) is not supported: the estimators always start from zeros")
         self.lstm.train()
-        if masks is not None:
-            return self._run(x, n_samples, N.MASK_INJECTED, masks)
-        return self._run(x, n_samples, N.MASK_PHILOX)
+        return self._run(x, n_samples, N.MASK_INJECTED if masks is not None else N.MASK_PHILOX, masks, hs)
 
 
 def ff_dims(state):
@@ -387,7 +470,7 @@ class ImuPoseLSTM:
 
     def __init__(self, input_size, hidden_layer_size=None, hidden_layer_count=None, output_size=None, dropout=0.2, philox_seed=None):
         self.input_size, self.output_size = int(input_size), int(output_size)
-        self._core = DropoutLSTM(self.WIDTH, self.WIDTH, self.DEPTH, self.output_size, dropout, philox_seed)
+        self._core = DropoutLSTM(self.WIDTH, self.WIDTH, self.DEPTH, self.output_size, dropout, philox_seed, lstm_variant="fp32")
         self.lstm = self._core.lstm
         self._state = None
         self._w_in = None                    # (W^T [I][256], b [256]) on the device, built lazily
@@ -433,46 +516,57 @@ class ImuPoseLSTM:
 
     __call__ = forward
 
-    def monte_carlo_predictions(self, n_samples, x):
+    def monte_carlo_predictions(self, n_samples, x, masks=None):
         """The reference's model has no MC dropout path: a regular forward pass (nn_models.py:247-252)."""
         return self(x, None)
 
+    # what the estimators read from any model they load (estimate/estimator.py)
+    @property
+    def dropout(self):
+        return self._core.dropout
+
+    @property
+    def philox_seed(self):
+        return self._core.philox_seed
+
+    @philox_seed.setter
+    def philox_seed(self, seed):
+        self._core.philox_seed = int(seed) & (2 ** 64 - 1)
+
+
+# results.json "model" names -> classes behind the same constructor keywords (nn_models.py:392-399)
+_MODEL_CLASSES = {"DropoutLSTM": DropoutLSTM, "DropoutFF": DropoutFF, "ImuPoseLSTM": ImuPoseLSTM}
+
+
+def _deploy_files(hash_str):
+    """``(results.json, checkpoint.pt)`` of a deployed model directory; a missing file is a ``UserWarning`` like the reference's."""
+    folder = Path(config.PATHS["deploy"]) / "nn" / hash_str
+    files = {"json": folder / "results.json", "checkpoint": folder / "checkpoint.pt"}
+    for kind, path in files.items():
+        if not path.exists():
+            raise UserWarning(f"no {kind} found {path}")
+    return files["json"], files["checkpoint"]
+
 
 def load_deployed_model_from_hash(hash_str: str):
-    """``(model, params)`` from ``<deploy>/nn/<hash>/{results.json, checkpoint.pt}`` (nn_models.py:373-415);
-    the checkpoint is the ``(model_state, optimizer_state)`` tuple the reference saves."""
-    save_path = Path(config.PATHS["deploy"]) / "nn" / hash_str
-    json_path, chkpt_path = save_path / "results.json", save_path / "checkpoint.pt"
-    if not json_path.exists():
-        raise UserWarning(f"no json found {json_path}")
-    if not chkpt_path.exists():
-        raise UserWarning(f"no checkpoint found {chkpt_path}")
-    with open(json_path, "r") as f:
-        params = json.load(f)
-    if params["model"] == "DropoutLSTM":
-        params["model"] = DropoutLSTM
-    elif params["model"] == "DropoutFF":
-        params["model"] = DropoutFF
-    elif params["model"] == "ImuPoseLSTM":
-        params["model"] = ImuPoseLSTM
-    else:
-        raise UserWarning(f"{params['model']} not handled")
-    nn_model = params["model"](
-        input_size=len(params["x_inputs_v"]),
-        hidden_layer_size=params["hidden_layer_size"],
-        hidden_layer_count=params["hidden_layer_count"],
-        output_size=len(params["y_targets_v"]),
-        dropout=params["dropout"],
-    )
-    model_state, _ = torch.load(chkpt_path, map_location="cpu")
-    nn_model.load_state_dict(model_state)
-    nn_model.eval()
-    logging.info("loaded model in eval mode from {}".format(save_path))
-    return nn_model, params
+    """``(model, params)`` of the deployed model ``<deploy>/nn/<hash_str>`` - what nn_models.py:373-415 returns: the parameter
+    dictionary of ``results.json`` with ``params["model"]`` replaced by the class, and an instance of that class in eval mode
+    holding the weights of ``checkpoint.pt`` (the ``(model_state, optimizer_state)`` pair the training code saved)."""
+    json_path, checkpoint_path = _deploy_files(hash_str)
+    params = json.loads(json_path.read_text())
+    try:
+        cls = _MODEL_CLASSES[params["model"]]
+    except KeyError:
+        raise UserWarning(f"{params['model']} not handled") from None
+    params["model"] = cls
+    model = cls(input_size=len(params["x_inputs_v"]), output_size=len(params["y_targets_v"]),
+                **{k: params[k] for k in ("hidden_layer_size", "hidden_layer_count", "dropout")})
+    weights = torch.load(checkpoint_path, map_location="cpu")[0]
+    model.load_state_dict(weights).eval()
+    logging.info("loaded model in eval mode from %s", json_path.parent)
+    return model, params
 
 
 def get_nn_name(params):
-    """SHA-1 of the parameter dictionary's ``str`` (nn_models.py:418-424)."""
-    sha1 = hashlib.sha1()
-    sha1.update(str(params).encode("utf-8"))
-    return str(sha1.hexdigest())
+    """Directory name of a model: SHA-1 hex digest of ``str(params)`` (nn_models.py:418-424)."""
+    return hashlib.sha1(str(params).encode("utf-8")).hexdigest()

@@ -78,6 +78,15 @@ int ape_features(const float* raw, int layout, int kind, const double* xx_m, con
                  int normalize, float* feats, int B, int nF, int frame0, const int32_t* stream_frames,
                  int feat_ring, void* stream);
 
+/*
+ * The window update of add_xx_to_row_hist_and_make_prediction (estimator.py:93-104) for callers that use the reference's three
+ * per-frame calls one by one: xx [B][I] float64 feature rows as parse_row_to_xx returned them -> z-score -> slot
+ * frame % feat_ring of each stream's ring (frames before 0 are never written: readers clamp to frame 0, which is the
+ * reference's "repeat the first row").
+ */
+int ape_features_push(const double* xx, int I, const double* xx_m, const double* xx_s, int normalize, float* feats,
+                      int B, int frame0, const int32_t* stream_frames, int feat_ring, void* stream);
+
 /* ---- stage 2: MC-dropout LSTM regressor -------------------------------------------------------- */
 /*
  * Replaces DropoutLSTM.forward / .monte_carlo_predictions (nn_models.py:180-207) and the
@@ -125,6 +134,19 @@ typedef struct ape_lstm_args {
     int trace_layer;
     /* per-stream frame counters [B] on the device (null: every stream is at frame0); < 0: skip the stream */
     const int32_t* stream_frames;
+    /* ---- ABI 5 ---- */
+    /* tensor-core path: E = B * nF of the LARGEST call that uses this workspace (0: this call's own E).  The offsets of the
+       buffers inside the workspace are computed from it, so calls of different sizes that are in flight on different streams
+       (the cross-call pipeline, estimate/batched.py) agree on where the two copies of layer 0's output live. */
+    int ws_E;
+    /* tensor-core path, H = 128, L >= 3: how consecutive layers >= 1 are launched.  0 = automatic (a pair of layers runs as ONE
+       two-layer wavefront launch, csrc/ape_lstm_tcw.cu, when the batch fills the GPU), 1 = one launch per layer always,
+       2 = wavefront pairs always */
+    int tc_flags;
+    /* fp32 path: optional initial state (h_0, c_0) of torch.nn.LSTM(x, hs) (nn_models.py:180-189): [L][E][H] float32 each, both
+       or neither; needs n_samples == 1 (a caller with per-sample states passes the samples as estimates) */
+    const float* h0;
+    const float* c0;
 } ape_lstm_args;
 
 int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
@@ -132,14 +154,19 @@ int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_
 int ape_mc_lstm_fma(const ape_lstm_args* args, void* stream);
 /*
  * Tensor-core variant (tcgen05, cta_group::2, TMEM accumulators): fp16 operands, fp32 accumulation and cell state.
- * H in {64, 128} (gate weights resident in shared memory) or 256 (gate weights streamed from L2 through a TMA ring),
- * L >= 2, all_steps == 0; same arguments and outputs as ape_mc_lstm_fma plus weights_tc.
+ * H in {64, 128} (gate weights resident in shared memory; H = 128, L >= 3: pairs of layers >= 1 as one two-layer wavefront launch
+ * with weights streamed from L2) or 256 (gate weights streamed from L2 through a cp.async.bulk ring), L >= 2; same arguments and
+ * outputs as ape_mc_lstm_fma plus weights_tc (h0 / c0 are not taken: a caller-supplied initial state runs on the fp32 path).
  * Use when the streams x MC-samples batch is large (>= a few thousand rows); the fp32 variant is the exact path.
  */
 int ape_mc_lstm_tc_supported(int I, int H, int L, int O);
 int ape_lstm_tc_blob_bytes(int I, int H, int L, int64_t* bytes);
 int ape_mc_lstm_tc_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
+/* workspace of a call with all_steps != 0 (keeps the last layer's sequence for the per-step output layer) */
+int ape_mc_lstm_tc_workspace_bytes_all_steps(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
 int ape_mc_lstm_tc(const ape_lstm_args* args, void* stream);
+/* number of kernels ape_mc_lstm_tc launches for these arguments (layer pairs of an H = 128 model count once) */
+int ape_mc_lstm_tc_launch_count(const ape_lstm_args* args, int* launches);
 /*
  * The Bernoulli keep-masks APE_MASK_PHILOX draws, written out as bytes in the APE_MASK_INJECTED layout
  * [E][L-1][T][n_samples][H] - lets a checker replay a Philox run through any injected-mask implementation.
