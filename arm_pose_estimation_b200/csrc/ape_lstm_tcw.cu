@@ -46,7 +46,13 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS;   // leader CTA: two MMA issuers (issuer k owns accumulator slot k);
 constexpr int N_ISSUERS = 2;                       //   peer CTA: the first of them forwards "piece landed" to the leader
 constexpr int TMA_WARP = MMA_WARP + N_ISSUERS;     // one lane per CTA fills the weight ring
-constexpr int THREADS = (TMA_WARP + 1) * 32;       // 736
+constexpr int THREADS = (TMA_WARP + 2) * 32;       // 768 = 6 warpgroups (one idle warp pads the last one: setmaxnreg works per warpgroup)
+// Register file re-balanced per role (launch allocation 80 x 768): the epilogue's working set (accumulator columns, gate values,
+// prefetched cell state) spilled ~20 values per half-pass at 80 registers
+constexpr int REGS_EPI = 96, REGS_LOAD = 48, REGS_MMA = 40;
+static_assert(512 * REGS_EPI + 128 * REGS_LOAD + 128 * REGS_MMA <= 768 * 80, "the re-balanced register file must fit the launch allocation");
+#define TCW_REG_INC(n) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(n))
+#define TCW_REG_DEC(n) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(n))
 constexpr int ROWS = 128;
 constexpr uint32_t KG_BYTES_B = 64 * 16;           // one k-group of a 64-column weight tile
 constexpr uint32_t PIECE_BYTES = KG * KG_BYTES_B;  // 16 KB: one operand half of one chunk = one ring slot
@@ -54,12 +60,13 @@ constexpr uint32_t CHUNK_BYTES = 2 * PIECE_BYTES;  // x k-groups then h k-groups
 constexpr uint32_t LAYER_BYTES = NCHL * CHUNK_BYTES;   // one CTA's half of a layer
 constexpr uint32_t A_BYTES = KG * ROWS * 16;       // one operand tile (32 KB)
 constexpr uint32_t MASK_BYTES = KG * ROWS * 4;     // keep-bit words of one item
-constexpr int NP = 7;                              // ring depth (slots)
+constexpr int NP = 6;                              // ring depth (slots)
+constexpr uint32_t BIAS_BYTES = 2 * 4 * H * 4;     // both layers' scaled bias
 constexpr int NFULL = 8;                           // "piece landed" barriers, indexed by piece number (> NP: never alias)
 constexpr uint32_t OUT_N = 32;                     // output product: 16 outputs x {fp16(W_o), W_o - fp16(W_o)}
 constexpr uint32_t OUT_BYTES = KG * (OUT_N / 2) * 16;   // this CTA's tile of it (4 KB)
 constexpr uint32_t BAR_BLOCK_BYTES = 512;
-constexpr uint32_t SMEM = A_BYTES + 2 * A_BYTES + 2 * MASK_BYTES + NP * PIECE_BYTES + BAR_BLOCK_BYTES;
+constexpr uint32_t SMEM = A_BYTES + 2 * A_BYTES + 2 * MASK_BYTES + NP * PIECE_BYTES + BIAS_BYTES + BAR_BLOCK_BYTES;
 constexpr uint32_t ACC_COLS = 256, HA_COL = 256, HB_COL = 384, H_COLS = H / 2, TMEM_COLS = 512;
 constexpr size_t CSTATE_FLOATS = (size_t)2 * H * ROWS;     // per CTA: [layer][k-group * 2 + half][row] float4
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -92,7 +99,8 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
     uint8_t* sX2 = sX1 + A_BYTES;                              // [2][A_BYTES] dropout(h_A) of item i in buffer i & 1
     uint32_t* sMask = reinterpret_cast<uint32_t*>(sX2 + 2 * A_BYTES);   // [2][KG][ROWS] keep-bit words of item i in buffer i & 1
     uint8_t* sW = reinterpret_cast<uint8_t*>(sMask) + 2 * MASK_BYTES;   // [NP][PIECE_BYTES] weight ring
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + NP * PIECE_BYTES);
+    float* sBias = reinterpret_cast<float*>(sW + NP * PIECE_BYTES);     // [2][4H] column 4u+g, scaled for the tanh form
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * 4 * H);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -103,6 +111,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
     const bool has_out = b.preds != nullptr;
 
     tc::timeline_stamp(a.timeline, 0);
+    for (int i = tid; i < 4 * H; i += THREADS) { sBias[i] = a.bias_s[i]; sBias[4 * H + i] = b.bias_s[i]; }
     if (warp == MMA_WARP) {
         tmem_alloc<2>(tmem_slot, TMEM_COLS);
         tmem_relinquish<2>();
@@ -132,12 +141,34 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
     tc::timeline_stamp(a.timeline, 1);
 
     if (warp < EPI_WARPS) {
+        TCW_REG_INC(REGS_EPI);
         // =================================== epilogue warps ===========================================================
         // warp (q, s): rows 32q..32q+31 (its TMEM lane quarter) x the 8 hidden units 8s..8s+7 of EVERY 32-unit chunk of both layers.
         const int q = warp & 3, s = warp >> 2;
         const int row_l = 32 * q + lane;
         const uint32_t t_lane = (uint32_t)(32 * q) << 16;
-        float4* cst0 = reinterpret_cast<float4*>(a.cstate + (size_t)blockIdx.x * CSTATE_FLOATS) + row_l;   // layer A; layer B: + 2 * KG * ROWS
+        // everything a half-pass addresses is (one per-thread base) + (a compile-time offset):
+        // (the empty asm statements make the bases opaque: the compiler then keeps them in registers instead of re-deriving
+        // them from the thread / CTA index in every half-pass, which had been a fifth of the epilogue's instructions)
+        unsigned long long cst_base = reinterpret_cast<unsigned long long>(
+            reinterpret_cast<float4*>(a.cstate + (size_t)blockIdx.x * CSTATE_FLOATS) + (size_t)(2 * s) * ROWS + row_l);
+        uint32_t bias_base = smem_u32(sBias + 32 * s);
+        uint32_t acc0 = tmem + t_lane + (uint32_t)(32 * s);                          // this thread's accumulator columns of a slot
+        uint32_t hst0 = tmem + t_lane + (uint32_t)(4 * s);                           // ... its 4 columns of an h buffer (+ 16 per chunk)
+        uint32_t x2_base = smem_u32(sX2) + unit_offset(ROWS, row_l, s);              // ... its unit of an x2 tile (+ 4 k-groups per chunk)
+        uint32_t mask_base = smem_u32(sMask + (size_t)s * ROWS + row_l);
+        uint32_t bars_local = smem_u32(bars), bars_leader;                           // barrier blocks: own CTA's, the leader's (cluster address)
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bars_leader) : "r"(bars_local), "r"(0));
+        asm volatile("" : "+l"(cst_base), "+r"(bias_base), "+r"(acc0), "+r"(hst0), "+r"(x2_base), "+r"(mask_base), "+r"(bars_local), "+r"(bars_leader));
+        float4* const cst0 = reinterpret_cast<float4*>(cst_base);
+        auto arrive_leader = [&](int bar) {
+            asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bars_leader + (uint32_t)bar * 8u) : "memory");
+        };
+        auto wait_bar = [&](int bar, uint32_t parity) {        // spin with the watchdog (a protocol bug traps instead of hanging)
+            uint32_t spins = 0;
+            while (!mbar_try_wait_addr(bars_local + (uint32_t)bar * 8u, parity)) { if (++spins > MBAR_WD_SPINS) __trap(); }
+        };
+        auto lds128 = [](uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; };
         uint32_t ph_out = 0;
         int tA = 0, tB = -1, tileB = cluster_id - n_clusters;  // advanced at the top of every wave
 
@@ -147,72 +178,59 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             if (B_on) { if (++tB == T) tB = 0; if (tB == 0) tileB += n_clusters; }
             const bool final_out = B_on && has_out && tB == T - 1;
             const uint32_t bufA = (uint32_t)w & 1u;            // x2 / mask buffer of A's item
-            if (A_on) mbar_wait_wd(&bars[BAR_MASK_READY + bufA], ((uint32_t)w >> 1) & 1u);
+            if (A_on) wait_bar(BAR_MASK_READY + (int)bufA, ((uint32_t)w >> 1) & 1u);
 
             const int hp_begin = A_on ? 0 : 2 * NCHL, hp_end = B_on ? 4 * NCHL : 2 * NCHL;
-            uint32_t rbuf[2][16];
+            // One set of 16 accumulator registers and ONE load site per half-pass: the second half of a chunk is requested as soon as
+            // the gate pre-activations of the first half have been formed (the load runs under the transcendentals and the cell
+            // update); the first half of the NEXT chunk at the end of this chunk's second half-pass, behind a blocking wait for that
+            // chunk (it was issued long ago - only its slot's refill, one chunk of MMAs, can still be outstanding).
+            uint32_t r[16];
             float4 cbuf[2];
-            float4 bnext[4];
             float hlo[4];
-            bool prefetched = true;
             auto t_of = [&](int layer) { return layer ? tB : tA; };
-            auto request_bias = [&](int hp1) {
-                const float* bs = (hp1 >> 3) ? b.bias_s : a.bias_s;
-                const float4* bias4 = reinterpret_cast<const float4*>(bs + (((hp1 >> 1) & 3) * 32 + 8 * s + 4 * (hp1 & 1)) * 4);
-                bnext[0] = __ldg(bias4); bnext[1] = __ldg(bias4 + 1); bnext[2] = __ldg(bias4 + 2); bnext[3] = __ldg(bias4 + 3);
-            };
-            auto cst_at = [&](int hp1) {                       // this thread's float4 of cell state of half-pass hp1
-                return cst0 + (size_t)((hp1 >> 3) * 2 * KG + (4 * ((hp1 >> 1) & 3) + s) * 2 + (hp1 & 1)) * ROWS;
+            auto cst_at = [&](int hp1) {                       // this thread's float4 of cell state of half-pass hp1: [layer][k-group * 2 + half][row]
+                return cst0 + (size_t)((hp1 >> 3) * 2 * KG + 8 * ((hp1 >> 1) & 3) + (hp1 & 1)) * ROWS;
             };
             cbuf[0] = cbuf[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (t_of(hp_begin >> 3) > 0) cbuf[0] = __ldcg(cst_at(hp_begin));
-            request_bias(hp_begin);
-            mbar_wait_wd(&bars[BAR_ACC_READY + 0], 0);          // every group of 4 chunks uses each slot twice: parity = (chunk >> 1) & 1
+            wait_bar(BAR_ACC_READY + 0, 0);                     // every group of 4 chunks uses each slot twice: parity = (chunk >> 1) & 1
             fence_after_sync();
-            tmem_ld_x16(tmem + t_lane + (uint32_t)(32 * s), rbuf[0]);
+            tmem_ld_x16(acc0, r);
 #pragma unroll
             for (int hp = 0; hp < 4 * NCHL; ++hp) {
                 if (hp < hp_begin || hp >= hp_end) continue;
                 const int layer = hp >> 3, cl = (hp >> 1) & 3, half = hp & 1, slot = (hp >> 1) & 1;
                 const int t_cur = t_of(layer);
-                const uint32_t* r = rbuf[hp & 1];
-                const float4 bsv[4] = {bnext[0], bnext[1], bnext[2], bnext[3]};
-                if (half == 0 && hp > hp_begin && !prefetched) {       // the chunk was not complete yet when the last half-pass looked
-                    mbar_wait_wd(&bars[BAR_ACC_READY + slot], (uint32_t)(cl >> 1));
-                    fence_after_sync();
-                    tmem_ld_x16(tmem + t_lane + (uint32_t)(slot * 128 + 32 * s), rbuf[hp & 1]);
-                }
                 tmem_ld_wait();
+                // gate pre-activations in the tanh form: sigmoid(x) = 0.5 + 0.5 tanh(x / 2); bias stored as 0.5 b (i, f, o), b (g)
+                float tg[16];
+                {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint4 bs = lds128(bias_base + (uint32_t)((layer * 4 * H + cl * 128 + half * 16 + 4 * u) * 4));
+                        tg[4 * u + 0] = fmaf(__uint_as_float(r[4 * u + 0]), 0.5f, __uint_as_float(bs.x));
+                        tg[4 * u + 1] = fmaf(__uint_as_float(r[4 * u + 1]), 0.5f, __uint_as_float(bs.y));
+                        tg[4 * u + 2] = __uint_as_float(r[4 * u + 2]) + __uint_as_float(bs.z);
+                        tg[4 * u + 3] = fmaf(__uint_as_float(r[4 * u + 3]), 0.5f, __uint_as_float(bs.w));
+                    }
+                }
                 if (half == 1) {                               // chunk fully drained: its issuer may refill the slot
                     fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&bars[BAR_SLOT_FREE + slot], rank);
+                    if (lane == 0) arrive_leader(BAR_SLOT_FREE + slot);
                 }
-                if (hp + 1 < hp_end) {
-                    const int hp1 = hp + 1, cl1 = (hp1 >> 1) & 3, h1 = hp1 & 1, slot1 = (hp1 >> 1) & 1;
-                    cbuf[hp1 & 1] = t_of(hp1 >> 3) > 0 ? __ldcg(cst_at(hp1)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    prefetched = true;
-                    if (half == 1) {                           // next chunk: prefetch its accumulators only if it is already complete
-                        prefetched = __all_sync(0xffffffffu, mbar_test_wait_addr(smem_u32(&bars[BAR_ACC_READY + slot1]), (uint32_t)(cl1 >> 1)));
-                        if (prefetched) fence_after_sync();
-                    }
-                    if (prefetched) tmem_ld_x16(tmem + t_lane + (uint32_t)(slot1 * 128 + 32 * s + 16 * h1), rbuf[hp1 & 1]);
-                }
-                const int j = 4 * cl + s;                      // k-group of units 32 cl + 8 s .. + 7
-                uint32_t mw = 0;
-                if (layer == 0 && half == 1) mw = sMask[(bufA * KG + (uint32_t)j) * ROWS + row_l];
-
-                // 5 MUFU per cell: sigmoid(x) = 0.5 + 0.5 tanh(x / 2) with the hardware tanh; bias stored as 0.5 b (i, f, o), b (g)
-                float hv[4], cn[4], tg[16];
                 const float cp[4] = {cbuf[hp & 1].x, cbuf[hp & 1].y, cbuf[hp & 1].z, cbuf[hp & 1].w};
+                if (hp + 1 < hp_end) cbuf[(hp + 1) & 1] = t_of((hp + 1) >> 3) > 0 ? __ldcg(cst_at(hp + 1)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (half == 0) tmem_ld_x16(acc0 + (uint32_t)(slot * 128 + 16), r);
+                uint32_t mw = 0;
+                if (layer == 0 && half == 1)
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mw) : "r"(mask_base + (bufA * KG + 4u * (uint32_t)cl) * (ROWS * 4)));
+
+                // 5 MUFU per cell
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float4 bs = bsv[u];
-                    tg[4 * u + 0] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 0]), 0.5f, bs.x));
-                    tg[4 * u + 1] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 1]), 0.5f, bs.y));
-                    tg[4 * u + 2] = tanh_approx(__uint_as_float(r[4 * u + 2]) + bs.z);
-                    tg[4 * u + 3] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 3]), 0.5f, bs.w));
-                }
+                for (int i = 0; i < 16; ++i) tg[i] = tanh_approx(tg[i]);
+                float hv[4], cn[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float gi = fmaf(tg[4 * u + 0], 0.5f, 0.5f), gf = fmaf(tg[4 * u + 1], 0.5f, 0.5f);
@@ -220,7 +238,6 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) hv[u] = fmaf(tg[4 * u + 3], 0.5f, 0.5f) * tanh_approx(cn[u]);
-                if (hp + 1 < hp_end) request_bias(hp + 1);
                 if (t_cur + 1 < T) __stcg(cst_at(hp), make_float4(cn[0], cn[1], cn[2], cn[3]));
 
                 if (half == 0) {
@@ -230,39 +247,44 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                     // h_A(t): fp16 pairs into the TMEM operand buffer of A's next step; dropout(h_A(t)) * 1/(1-p) as fp16 units into
                     // B's input tile (the scale is applied BEFORE the rounding, as the one-layer kernel does for its out_units)
                     if (t_cur + 1 < T)
-                        tmem_st_x4(tmem + t_lane + HA_COL + (uint32_t)((t_cur + 1) & 1) * H_COLS + (uint32_t)(4 * j),
+                        tmem_st_x4(hst0 + HA_COL + (uint32_t)((t_cur + 1) & 1) * H_COLS + (uint32_t)(16 * cl),
                                    pack_half2(hlo[0], hlo[1]), pack_half2(hlo[2], hlo[3]), pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]));
                     const float os = a.out_scale;
                     const uint32_t mw2 = mw << 1;
-                    *reinterpret_cast<uint4*>(sX2 + bufA * A_BYTES + unit_offset(ROWS, row_l, j)) =
-                        make_uint4(pack_half2(hlo[0] * os, hlo[1] * os) & prmt(mw, 0u, 0x9988u), pack_half2(hlo[2] * os, hlo[3] * os) & prmt(mw, 0u, 0xBBAAu),
-                                   pack_half2(hv[0] * os, hv[1] * os) & prmt(mw2, 0u, 0x9988u), pack_half2(hv[2] * os, hv[3] * os) & prmt(mw2, 0u, 0xBBAAu));
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(x2_base + bufA * A_BYTES + (uint32_t)(4 * cl) * (ROWS * 16)),
+                                 "r"(pack_half2(hlo[0] * os, hlo[1] * os) & prmt(mw, 0u, 0x9988u)), "r"(pack_half2(hlo[2] * os, hlo[3] * os) & prmt(mw, 0u, 0xBBAAu)),
+                                 "r"(pack_half2(hv[0] * os, hv[1] * os) & prmt(mw2, 0u, 0x9988u)), "r"(pack_half2(hv[2] * os, hv[3] * os) & prmt(mw2, 0u, 0xBBAAu)) : "memory");
                     if (t_cur + 1 < T) tmem_st_wait();
                     fence_proxy_async_smem();
                     fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&bars[BAR_HA_READY + cl], rank);
+                    if (lane == 0) arrive_leader(BAR_HA_READY + cl);
                 } else {
                     if (t_cur + 1 < T || final_out) {
-                        tmem_st_x4(tmem + t_lane + HB_COL + (uint32_t)((t_cur + 1) & 1) * H_COLS + (uint32_t)(4 * j),
+                        tmem_st_x4(hst0 + HB_COL + (uint32_t)((t_cur + 1) & 1) * H_COLS + (uint32_t)(16 * cl),
                                    pack_half2(hlo[0], hlo[1]), pack_half2(hlo[2], hlo[3]), pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]));
                         tmem_st_wait();
                     }
                     if (b.out_units) {
                         const float os = b.out_scale;
-                        b.out_units[((((size_t)tileB * T + t_cur) * 2 + rank) * KG + j) * ROWS + row_l] =
+                        b.out_units[((((size_t)tileB * T + t_cur) * 2 + rank) * KG + 4 * cl + s) * ROWS + row_l] =
                             make_uint4(pack_half2(hlo[0] * os, hlo[1] * os), pack_half2(hlo[2] * os, hlo[3] * os),
                                        pack_half2(hv[0] * os, hv[1] * os), pack_half2(hv[2] * os, hv[3] * os));
                     }
                     fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&bars[BAR_HB_READY + cl], rank);
+                    if (lane == 0) arrive_leader(BAR_HB_READY + cl);
+                }
+                if (half == 1 && hp + 1 < hp_end) {            // the next chunk's first half
+                    wait_bar(BAR_ACC_READY + ((slot + 1) & 1), (uint32_t)((((hp + 1) >> 1) & 3) >> 1));
+                    fence_after_sync();
+                    tmem_ld_x16(acc0 + (uint32_t)(((slot + 1) & 1) * 128), r);
                 }
             }
             if (final_out) {                                   // output_layer (nn_models.py:189), last step of the last layer only
                 // Issuer 0 multiplies the published h_T (TMEM) by [fp16(W_o) | W_o - fp16(W_o)]^T (one extra ring piece, N = 32) into
                 // the first 32 columns of B's OTHER h buffer - it held h_{T-1}, which nothing reads any more.
-                mbar_wait_wd(&bars[BAR_OUT_READY], ph_out);
+                wait_bar(BAR_OUT_READY, ph_out);
                 ph_out ^= 1;
                 fence_after_sync();
                 uint32_t o32[32];                              // columns 0..15: h_T x fp16(W_o)^T, 16..31: h_T x (W_o - fp16(W_o))^T
@@ -285,11 +307,12 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             }
         }
     } else if (warp < MMA_WARP) {
+        TCW_REG_DEC(REGS_LOAD);
         // =================================== loader warps: x1 of item i, keep-bit words of item i ============================
         // One thread per row.  Item i's x1 tile may be written once the x-parts of item i-1 have retired (X1_DONE); the loads and
         // the Philox draws of the first half of the row are done before that wait.
         const int row_l = tid - EPI_THREADS;
-        constexpr int BK = 8;
+        constexpr int BK = 4;                                  // k-groups per batch of loads (register budget of the loader warps)
         int t = -1, tile = cluster_id - n_clusters;
         int e = 0, smp = 0, bidx = 0, f = 0;
         bool valid = false;
@@ -362,7 +385,9 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[BAR_MASK_READY + (i & 1)]);
         }
-    } else if (warp < TMA_WARP) {
+    } else {
+      TCW_REG_DEC(REGS_MMA);            // (issuers, ring producer and the idle warp that pads their warpgroup)
+      if (warp < TMA_WARP) {
         if (rank == 0) {
             // =============================== MMA issuers (leader CTA; the whole warp runs, one elected lane issues) =====
             // Issuer k owns accumulator slot k, i.e. chunks 1, 3 (k = 1) or 0, 2 (k = 0) of every layer group.  Both walk the whole
@@ -479,7 +504,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             }
             if (has_out) forward();
         }
-    } else if (lane == 0) {
+      } else if (warp == TMA_WARP && lane == 0) {
         // =================================== weight-ring producer (one lane per CTA) =====================================
         const uint8_t* WA = a.W + (size_t)rank * LAYER_BYTES;  // this CTA's half of each layer's weight tiles
         const uint8_t* WB = b.W + (size_t)rank * LAYER_BYTES;
@@ -509,6 +534,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             }
         }
         if (has_out) put(b.Wo16 + (size_t)rank * OUT_BYTES, OUT_BYTES);
+      }
     }
     __syncwarp();
     fence_before_sync();

@@ -112,10 +112,11 @@ def pad_recordings(recordings):
     return out, lengths
 
 
-def relabel_recordings(recordings, make_estimator, frames_per_call=16, keep_samples=False):
+def relabel_recordings(recordings, make_estimator, frames_per_call=16, keep_samples=False, masks=None):
     """Offline relabelling: ``recordings`` = list of ``[frames_i, ncols]`` arrays (or one ``[R, F, ncols]`` array);
     ``make_estimator(n_streams, frames_per_call)`` returns a ``BatchedEstimator``.  Returns a list of dicts with
-    ``msg [frames_i, 25]``, ``std [frames_i, 6]`` (and ``samples`` if asked).  The next calls are staged and enqueued while call k runs."""
+    ``msg [frames_i, 25]``, ``std [frames_i, 6]`` (and ``samples`` if asked).  The next calls are staged and enqueued while call k runs.
+    ``masks``: explicit dropout masks ``[R, F, L-1, T, n, H]`` for an estimator built with ``MASK_INJECTED`` (parity runs)."""
     if isinstance(recordings, np.ndarray) and recordings.ndim == 3:
         rows, lengths = np.asarray(recordings, dtype=np.float32), np.full(len(recordings), recordings.shape[1], np.int64)
     else:
@@ -140,7 +141,7 @@ def relabel_recordings(recordings, make_estimator, frames_per_call=16, keep_samp
     outstanding = []                                          # submitted, not yet collected (oldest first)
     for f0 in range(0, F, be.nF_max):
         nf = min(be.nF_max, F - f0)
-        outstanding.append((be.submit(rows[:, f0:f0 + nf]), f0, nf))
+        outstanding.append((be.submit(rows[:, f0:f0 + nf], masks=None if masks is None else masks[:, f0:f0 + nf]), f0, nf))
         if len(outstanding) >= be.N_SLOTS - 1:                # the next submit reuses the oldest one's staging slot
             collect(*outstanding.pop(0))
     for item in outstanding:

@@ -313,6 +313,57 @@ def golden_imu_pose_lstm():
     np.savez_compressed(HERE / "imu_pose_lstm.npz", x=x, y=y, y_mc=y_mc, weight_seed=99)
 
 
+def golden_csv():
+    print("file formats: the reference's own recorders write the watch-only golden rows / messages")
+    import queue
+    import threading
+    import time
+    from wear_mocap_ape.record.arm_pose_to_csv import arm_pose_to_csv
+    from wear_mocap_ape.record.est_output import EstOutputRecorder
+    from arm_pose_estimation_b200.record import replay
+    g = np.load(HERE / "e2e_watch_only_s3.npz")
+    rows, last = g["rows"], g["last"]
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp = Path(tmp)
+        # raw IMU recording (record/arm_pose_to_csv.py:9-32): rows arrive as tuples of Python floats (struct.unpack in the
+        # listener); the recorder loops forever, so a non-iterable sentinel ends its thread and closes the file
+        q = queue.Queue()
+        th = threading.Thread(target=arm_pose_to_csv, args=(q, tmp), daemon=True)
+        th.start()
+        for r in rows:
+            q.put(tuple(float(v) for v in r))
+        q.put(None)                                                   # (skipped by the recorder: arm_pose_to_csv.py:22)
+        q.put(0)                                                      # map(str, 0) raises -> the with-block closes the file
+        th.join(timeout=20)
+        (imu_file,) = list(tmp.glob("arm_pose_rec_*.csv"))
+        imu_text = imu_file.read_text()
+        # pose estimates (record/est_output.py:10-57)
+        rec = EstOutputRecorder(tmp / "est.csv")
+        mq = queue.Queue()
+        rec.record_in_thread(mq)
+        for m in last:
+            mq.put(np.asarray(m))
+        while not mq.empty():
+            time.sleep(0.05)
+        time.sleep(0.2)
+        rec.terminate()
+        time.sleep(2.5)                                               # (its queue.get times out after 2 s, then the loop ends)
+        est_text = (tmp / "est.csv").read_text()
+        # the package's reader / writer against them
+        back, layout = replay.read_imu_csv(imu_file)
+        assert layout == my_msg.LAYOUT_WATCH_ONLY
+        close(back, rows, 0, "read_imu_csv(reference recording)")
+        replay.write_imu_csv(tmp / "mine.csv", rows)
+        assert (tmp / "mine.csv").read_text() == imu_text, "write_imu_csv differs from the reference recorder's bytes"
+        times, msgs = replay.read_pose_csv(tmp / "est.csv")
+        close(msgs, last, 0, "read_pose_csv(reference EstOutputRecorder file)")
+        replay.write_pose_csv(tmp / "mine_est.csv", last, times=times)
+        assert (tmp / "mine_est.csv").read_text() == est_text, "write_pose_csv differs from EstOutputRecorder's bytes"
+    (HERE / "arm_pose_rec_watch_only_s3.csv").write_text(imu_text)
+    (HERE / "est_output_watch_only_s3.csv").write_text(est_text)
+    print("  ok csv fixtures written")
+
+
 def main():
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     with tempfile.TemporaryDirectory() as tmp:
@@ -323,6 +374,9 @@ def main():
         if only == "imu_pose_lstm":
             golden_imu_pose_lstm()
             return
+        if only == "csv":
+            golden_csv()
+            return
         golden_tables()
         golden_quat()
         golden_features()
@@ -331,6 +385,7 @@ def main():
         golden_e2e()
         golden_ff()
         golden_imu_pose_lstm()
+        golden_csv()
     print("fixtures written to", HERE)
 
 

@@ -1,6 +1,11 @@
-"""Recorded-IMU CSV replay front-end: file formats on the CPU, relabelling against the streaming path on the GPU."""
+"""Recorded-IMU CSV replay front-end: file formats on the CPU (against files written by the reference's own recorders),
+relabelling on the GPU against the reference's golden messages (injected masks) and against the streaming path."""
+from pathlib import Path
+
 import numpy as np
 import pytest
+
+from conftest import load_golden, unpack_masks
 
 from arm_pose_estimation_b200 import synthetic as syn
 from arm_pose_estimation_b200.data_types import messaging
@@ -79,3 +84,55 @@ def test_relabel_matches_streaming(tmp_path):
     assert [len(r["msg"]) for r in res] == [11, 7, 16]
     replay.write_pose_csv(tmp_path / "est0.csv", res[0]["msg"])
     np.testing.assert_array_equal(replay.read_pose_csv(tmp_path / "est0.csv")[1], res[0]["msg"])
+
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def test_reference_written_files_parse_and_round_trip(tmp_path):
+    # fixtures written by the reference's own arm_pose_to_csv / EstOutputRecorder (tests/golden/make_golden.py::golden_csv)
+    g = load_golden("e2e_watch_only_s3.npz")
+    rows, layout = replay.read_imu_csv(GOLDEN / "arm_pose_rec_watch_only_s3.csv")
+    assert layout == messaging.LAYOUT_WATCH_ONLY
+    np.testing.assert_array_equal(rows, g["rows"])
+    replay.write_imu_csv(tmp_path / "mine.csv", rows)                    # our writer produces the reference recorder's bytes
+    assert (tmp_path / "mine.csv").read_text() == (GOLDEN / "arm_pose_rec_watch_only_s3.csv").read_text()
+    times, msgs = replay.read_pose_csv(GOLDEN / "est_output_watch_only_s3.csv")
+    np.testing.assert_array_equal(msgs, g["last"])
+    replay.write_pose_csv(tmp_path / "mine_est.csv", msgs, times=times)
+    assert (tmp_path / "mine_est.csv").read_text() == (GOLDEN / "est_output_watch_only_s3.csv").read_text()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["fp32", "tc"])
+def test_relabel_of_the_reference_recording_gives_the_reference_messages(tmp_path, variant):
+    # the recording the REFERENCE wrote -> relabel_recordings (masks the reference drew, injected) -> the messages the reference
+    # computed frame by frame (golden), and the pose file its EstOutputRecorder wrote
+    from arm_pose_estimation_b200 import _native as N
+    from arm_pose_estimation_b200.estimate.batched import BatchedEstimator
+    from test_gpu_parity import msg_close, POS_TOL
+    g = load_golden("e2e_watch_only_s3.npz")
+    kind = syn.KIND_WATCH_ONLY
+    spec = syn.kind_spec(kind)
+    state = syn.synth_state_dict(spec["I"], spec["H"], spec["L"], spec["O"], int(g["weight_seed"]))
+    n, smooth = int(g["n"]), int(g["smooth"])
+    masks = unpack_masks(g)                                              # [F, L-1, T, n, H]
+    rows, _ = replay.read_imu_csv(GOLDEN / "arm_pose_rec_watch_only_s3.csv")
+
+    def make(n_streams, fpc):
+        return BatchedEstimator(kind=kind, layout=spec["layout"], state=state, seq_len=spec["T"], y_targets=spec["y_targets"],
+                                stats=spec["stats"], n_streams=n_streams, mc_samples=n, smooth=smooth, dropout=spec["p"],
+                                frames_per_call=fpc, mask_mode=N.MASK_INJECTED, lstm_variant=variant)
+    # two copies of the recording, one cut short: ragged recordings, calls of 4 + 4 + 4 + 2 frames
+    res = replay.relabel_recordings([rows, rows[:9]], make, frames_per_call=4, keep_samples=True,
+                                    masks=np.stack([masks, masks]))
+    assert [len(r["msg"]) for r in res] == [len(rows), 9]
+    worst = 0.0
+    for r in res:
+        F = len(r["msg"])
+        worst = max(worst, msg_close(r["msg"], g["msgs"][:F, :25]))
+        worst = max(worst, float(np.abs(r["samples"].reshape(F, -1) - g["msgs"][:F, 25:]).max()))
+    print(f"relabelled reference recording [{variant}]: worst position error vs the reference's messages {worst:.3g} m")
+    assert worst <= POS_TOL
+    replay.write_pose_csv(tmp_path / "est.csv", res[0]["msg"])
+    msg_close(replay.read_pose_csv(tmp_path / "est.csv")[1], replay.read_pose_csv(GOLDEN / "est_output_watch_only_s3.csv")[1])
