@@ -41,16 +41,16 @@ using tc::TcLayerArgs;
 using tc::tanh_approx;
 
 constexpr int H = 128, NCHL = H / 32, KG = H / 8;  // chunks per layer, k-groups per operand
-constexpr int EPI_WARPS = 16, LOAD_WARPS = 4;
+constexpr int EPI_WARPS = 16, LOAD_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS;   // leader CTA: two MMA issuers (issuer k owns accumulator slot k);
 constexpr int N_ISSUERS = 2;                       //   peer CTA: the first of them forwards "piece landed" to the leader
 constexpr int TMA_WARP = MMA_WARP + N_ISSUERS;     // one lane per CTA fills the weight ring
-constexpr int THREADS = (TMA_WARP + 2) * 32;       // 768 = 6 warpgroups (one idle warp pads the last one: setmaxnreg works per warpgroup)
-// Register file re-balanced per role (launch allocation 80 x 768): the epilogue's working set (accumulator columns, gate values,
+constexpr int THREADS = (TMA_WARP + 2) * 32;       // 896 = 7 warpgroups (one idle warp pads the last one: setmaxnreg works per warpgroup)
+// Register file re-balanced per role (launch allocation 72 x 896): the epilogue's working set (accumulator columns, gate values,
 // prefetched cell state) spilled ~20 values per half-pass at 80 registers
-constexpr int REGS_EPI = 96, REGS_LOAD = 48, REGS_MMA = 40;
-static_assert(512 * REGS_EPI + 128 * REGS_LOAD + 128 * REGS_MMA <= 768 * 80, "the re-balanced register file must fit the launch allocation");
+constexpr int REGS_EPI = 96, REGS_LOAD = 40, REGS_MMA = 40;
+static_assert(EPI_THREADS * REGS_EPI + LOAD_WARPS * 32 * REGS_LOAD + 128 * REGS_MMA <= THREADS * 72, "the re-balanced register file must fit the launch allocation");
 #define TCW_REG_INC(n) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(n))
 #define TCW_REG_DEC(n) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(n))
 constexpr int ROWS = 128;
@@ -309,10 +309,13 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
     } else if (warp < MMA_WARP) {
         TCW_REG_DEC(REGS_LOAD);
         // =================================== loader warps: x1 of item i, keep-bit words of item i ============================
-        // One thread per row.  Item i's x1 tile may be written once the x-parts of item i-1 have retired (X1_DONE); the loads and
-        // the Philox draws of the first half of the row are done before that wait.
-        const int row_l = tid - EPI_THREADS;
-        constexpr int BK = 4;                                  // k-groups per batch of loads (register budget of the loader warps)
+        // Two threads per row, 8 k-groups each (with one thread per row - 32 Philox draws per item on a single warp per SM
+        // quarter - the keep-bit words arrived late and the epilogue warps spent a sixth of their time waiting for them).  Item i's
+        // x1 tile may be written once the x-parts of item i-1 have retired (X1_DONE); the loads and the Philox draws of the first
+        // batch are done before that wait.
+        const int row_l = (tid - EPI_THREADS) & (ROWS - 1);
+        const int j0 = ((tid - EPI_THREADS) >> 7) * (KG / 2);  // this thread's k-groups: j0 .. j0 + 7
+        constexpr int BK = 2;                                  // k-groups per batch of loads (register budget of the loader warps)
         int t = -1, tile = cluster_id - n_clusters;
         int e = 0, smp = 0, bidx = 0, f = 0;
         bool valid = false;
@@ -331,7 +334,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             else src += ((((size_t)(e >> (a.in_rpc_shift + 1)) * T + t) * 2 + ((e >> a.in_rpc_shift) & 1)) * KG) * ROWS +
                         (e & ((1 << a.in_rpc_shift) - 1));
 #pragma unroll 1
-            for (int b0 = 0; b0 < KG; b0 += BK) {
+            for (int b0 = j0; b0 < j0 + KG / 2; b0 += BK) {
                 uint4 pre[BK];
 #pragma unroll
                 for (int jj = 0; jj < BK; ++jj) pre[jj] = valid ? __ldg(src + (size_t)(b0 + jj) * ROWS) : make_uint4(0, 0, 0, 0);
@@ -353,7 +356,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                         pre[jj].w &= ((m.y & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.y & 0xFF000000u) ? 0xFFFF0000u : 0u);
                     }
                 }
-                if (b0 == 0 && i >= 1) mbar_wait_wd(&bars[BAR_X1_DONE], ((uint32_t)(i - 1)) & 1u);
+                if (b0 == j0 && i >= 1) mbar_wait_wd(&bars[BAR_X1_DONE], ((uint32_t)(i - 1)) & 1u);
 #pragma unroll
                 for (int jj = 0; jj < BK; ++jj) *reinterpret_cast<uint4*>(sX1 + unit_offset(ROWS, row_l, b0 + jj)) = pre[jj];
             }
@@ -364,7 +367,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             // passes of item i-2: those ended before X1_DONE(i-1), which this thread has seen.
             uint32_t* mdst = sMask + (size_t)((uint32_t)i & 1u) * KG * ROWS + row_l;
 #pragma unroll 4
-            for (int j = 0; j < KG; ++j) {
+            for (int j = j0; j < j0 + KG / 2; ++j) {
                 uint32_t wbits = 0xC0C0C0C0u;
                 if (b.mask_mode == APE_MASK_PHILOX) {
                     wbits = keep_word(APE_PHILOX_DRAW(b, stream, (uint32_t)f, (uint32_t)smp, (uint32_t)b.gap, (uint32_t)t, (uint32_t)j, b.keep_thr16));

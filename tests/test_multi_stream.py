@@ -118,3 +118,22 @@ def test_every_stream_matches_its_own_single_stream_estimator(variant):
             out = solo.step(rows[b:b + 1, f:f + 1])
             want = np.concatenate([out.msg[0, 0].astype(np.float64), out.samples[0, 0].astype(np.float64).ravel()])
             np.testing.assert_array_equal(got[b][f], want)
+    # ... and the ORACLE's single-stream loop (estimator.py:155-178 restated), fed the masks the kernels drew for that stream
+    # (ape_philox_masks exports them: keyed by global stream id and the stream's own frame counter)
+    import torch
+    from oracle import estimator as OE
+    L, T, H = spec["L"], spec["T"], spec["H"]
+    worst = 0.0
+    for b in range(B):
+        masks = torch.empty((1, fed[b], L - 1, T, n, H), dtype=torch.uint8, device="cuda")
+        N.check(N.load().ape_philox_masks(11, b, 1, fed[b], 0, L, T, n, H, spec["p"], N.ptr(masks), N.current_stream_ptr()), "masks")
+        masks = masks.cpu().numpy()[0]
+        orc = OE.OracleEstimator(syn.KIND_NAMES[kind], spec["lookup"], state, spec["stats"], spec["y_targets"].name,
+                                 T, smooth, n, None, spec["p"], mask_source=lambda f, m=masks: list(m[f]))
+        for f in range(fed[b]):
+            want = np.asarray(orc.step(rows[b, f]), dtype=np.float64)
+            for a, c in ((4, 7), (11, 14), (18, 21)):                          # hand, elbow, shoulder positions
+                worst = max(worst, float(np.abs(got[b][f][a:c] - want[a:c]).max()))
+            worst = max(worst, float(np.abs(got[b][f][25:] - want[25:]).max()))
+    print(f"multi-stream front-end [{variant}] vs the oracle's per-stream loop: worst position error {worst:.3g} m")
+    assert worst <= 1e-4
