@@ -130,10 +130,30 @@ APE_HD PhiloxRoundKeys philox_round_keys(uint64_t seed) {
     return rk;
 }
 #ifdef __CUDACC__
-// philox_keep_halfmask with precomputed round keys: bit-identical draws
-__device__ __forceinline__ uint4 philox_keep_halfmask_rk(const PhiloxRoundKeys& rk, uint32_t stream, uint32_t frame, uint32_t sample,
-                                                         uint32_t gap, uint32_t t, uint32_t group, uint32_t keep_thr16) {
-    if (keep_thr16 >= 65536u) return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+// Keep FLAGS of the 8 lanes of a draw: bit 15 (low lane) and bit 31 (high lane) of word i are set iff that 16-bit lane is
+// < keep_thr16 - the same decision as `lane < keep_thr16` above, evaluated for both lanes of a word with three integer
+// operations instead of an emulated SIMD compare (the loader warps of the tensor-core kernels are issue-bound):
+//   lane < thr  <=>  thr.bit15 ? (lane.bit15 == 0 || lane.low15 < thr.low15) : (lane.bit15 == 0 && lane.low15 < thr.low15)
+//   lane.low15 < thr.low15  <=>  bit 15 of (0x7FFF + thr.low15 - lane.low15)   (no borrow between the lanes: 0 <= . <= 0xFFFE)
+struct KeepCompare { uint32_t k2, top; };      // k2: (0x7FFF + thr.low15) in both lanes; top: all ones iff thr.bit15
+__device__ __forceinline__ KeepCompare keep_compare(uint32_t keep_thr16) {
+    const uint32_t k = 0x7FFFu + (keep_thr16 & 0x7FFFu);
+    return {k | (k << 16), (keep_thr16 & 0x8000u) ? 0xFFFFFFFFu : 0u};
+}
+__device__ __forceinline__ uint32_t keep_flags_word(uint32_t c, const KeepCompare kc) {
+    const uint32_t d = kc.k2 - (c & 0x7FFF7FFFu);
+    return (~c & d) | (kc.top & (~c | d));     // one LOP3: top ? (~c | d) : (~c & d)
+}
+// flags (bits 15 / 31) -> half2 AND-mask (0xFFFF per kept lane): one byte permute with sign replication
+__device__ __forceinline__ uint32_t keep_flags_to_halfmask(uint32_t flags) {
+    uint32_t m;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(flags), "r"(0u), "r"(0xBB99u));
+    return m;
+}
+// the four flag words of one draw (Philox4x32-10 with precomputed round keys; counter layout of philox_keep8)
+__device__ __forceinline__ uint4 philox_keep_flags_rk(const PhiloxRoundKeys& rk, uint32_t stream, uint32_t frame, uint32_t sample,
+                                                      uint32_t gap, uint32_t t, uint32_t group, uint32_t keep_thr16) {
+    if (keep_thr16 >= 65536u) return make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
     uint32_t c0 = stream, c1 = frame, c2 = (sample & 0xFFFFFu) | ((gap & 0xFu) << 20) | ((t & 0xFFu) << 24), c3 = group;
 #pragma unroll
@@ -144,8 +164,14 @@ __device__ __forceinline__ uint4 philox_keep_halfmask_rk(const PhiloxRoundKeys& 
         const uint32_t n0 = hi1 ^ c1 ^ rk.k[2 * r], n2 = hi0 ^ c3 ^ rk.k[2 * r + 1];
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     }
-    const uint32_t thr2 = keep_thr16 | (keep_thr16 << 16);
-    return make_uint4(__vcmpltu2(c0, thr2), __vcmpltu2(c1, thr2), __vcmpltu2(c2, thr2), __vcmpltu2(c3, thr2));
+    const KeepCompare kc = keep_compare(keep_thr16);
+    return make_uint4(keep_flags_word(c0, kc), keep_flags_word(c1, kc), keep_flags_word(c2, kc), keep_flags_word(c3, kc));
+}
+// philox_keep_halfmask with precomputed round keys: bit-identical draws
+__device__ __forceinline__ uint4 philox_keep_halfmask_rk(const PhiloxRoundKeys& rk, uint32_t stream, uint32_t frame, uint32_t sample,
+                                                         uint32_t gap, uint32_t t, uint32_t group, uint32_t keep_thr16) {
+    const uint4 f = philox_keep_flags_rk(rk, stream, frame, sample, gap, t, group, keep_thr16);
+    return make_uint4(keep_flags_to_halfmask(f.x), keep_flags_to_halfmask(f.y), keep_flags_to_halfmask(f.z), keep_flags_to_halfmask(f.w));
 }
 #endif
 

@@ -555,6 +555,7 @@ extern "C" int ape_lstm_tc_blob_bytes(int I, int H, int L, int64_t* bytes) {
     int64_t total = 0;
     for (int l = 0; l < L; ++l) total += (int64_t)tc_layer_bytes(l, I, H);
     total += (int64_t)2 * (H / 8) * (H > 128 ? 32 : 16) * 16;              // fp16 output-layer tiles: 2 CTAs x [H/8][16 | 32 (H = 256) columns][8] halfs
+    if (L >= 3) total += (int64_t)(L - 1) * (int64_t)ape::tcw::layer_bytes(H);   // wavefront kernel's pieces of layers >= 1 (H = 128)
     *bytes = total;
     return APE_OK;
 }
@@ -668,8 +669,10 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
 
     const int H = g->H;
     const uint8_t* wl = (const uint8_t*)g->weights_tc;
-    const uint8_t* wo16 = wl;                                               // the fp16 output-layer tile sits after all layers
+    const uint8_t* wo16 = wl;                                               // the fp16 output-layer tile sits after all layers,
     for (int l = 0; l < g->L; ++l) wo16 += tc_layer_bytes(l, g->I, g->H);
+    const size_t ww_layer = g->L >= 3 ? ape::tcw::layer_bytes(g->H) : 0;     // ... then the wavefront kernel's pieces of layers 1 .. L-1
+    const uint8_t* ww = wo16 + (size_t)2 * (g->H / 8) * (g->H > 128 ? 32 : 16) * 16;
     const float scale = g->mask_mode == APE_MASK_NONE ? 1.0f : 1.0f / (1.0f - g->dropout_p);
     const bool all_steps = g->all_steps != 0;
     // argument block of layer l (`wl_l`: its weights inside the fp16 blob)
@@ -678,6 +681,7 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
         tc::TcLayerArgs a{};
         a.W = wl_l;
         a.bias_s = (const float*)(wl_l + tc_layer_bytes(l, g->I, H) - (size_t)4 * H * 4);
+        a.Ww = (ww_layer && l >= 1) ? ww + (size_t)(l - 1) * ww_layer : nullptr;
         a.T = g->T;
         a.kgx = tc_kgx(l, g->I, H);
         a.Kin = l == 0 ? g->I : H;

@@ -16,6 +16,9 @@ enum { IN_WINDOW_F32 = 0, IN_DENSE_F32 = 1, IN_SHARED_UNITS = 2, IN_UNITS = 3 };
 struct TcLayerArgs {
     const uint8_t* W;          // this layer: [cta 2][chunk][x k-groups then h k-groups][64 gate columns][8 halfs]
     const float* bias_s;       // [4H] column c = 4u+g, scaled for the tanh form: 0.5 b (i, f, o), b (g)
+    const uint8_t* Ww;         // wavefront kernel (H = 128, layers >= 1 of an L >= 3 model), else null: [cta 2][chunk 4][x-piece | h-piece]:
+                               // x-piece [16 + 2 k-groups][64][8] (i, f, o columns halved; k-group 16 rows 0, 1 = fp16(bias_s), remainder),
+                               // h-piece [16 k-groups][64][8] (i, f, o columns halved)
     int T, kgx, Kin;           // x-part: kgx k-groups (layer 0: ceil16(I)/8, else H/8) of which Kin columns are real
     int rpc;                   // rows per CTA actually used (128, or 32 to spread a small layer 0 over more SMs)
     int in_rpc_shift;          // IN_SHARED_UNITS: log2(rpc) of the producing layer
@@ -114,6 +117,7 @@ int launch_layer(int H, const tc::TcLayerArgs& a, int sm_count, cudaStream_t st)
 namespace tcw {
 // two-layer wavefront kernel (ape_lstm_tcw.cu): layers a and b = a + 1 of an H = 128 model in one launch
 bool supported(int H, int T, int O);
+size_t layer_bytes(int H);                      // bytes of one layer's pieces (TcLayerArgs::Ww)
 size_t scratch_bytes(int H, int sm_count);      // per-CTA cell-state scratch of one launch
 int launch_pair(const tc::TcLayerArgs& a, const tc::TcLayerArgs& b, int sm_count, cudaStream_t st);
 }  // namespace tcw

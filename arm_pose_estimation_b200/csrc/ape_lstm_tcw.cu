@@ -15,16 +15,21 @@
 // launch pays one half-wave of fill and drain in total.
 //
 // What lives where (per CTA = 128 rows; one row per TMEM lane):
-//   * gate weights of BOTH layers (2 x 128 KB per CTA) stream from L2 through a shared-memory ring of 16 KB slots filled by one
+//   * gate weights of BOTH layers (2 x 136 KB per CTA) stream from L2 through a shared-memory ring of 18 KB slots filled by one
 //     thread with bulk asynchronous copies (cp.async.bulk, mbarrier complete_tx; as in ape_lstm_tcs.cu).  A piece is one
-//     operand half (x- or recurrent part, K = 128) of this CTA's 64 gate columns of a 32-unit chunk = 8 MMAs;
+//     operand half (x- or recurrent part, K = 128) of this CTA's 64 gate columns of a 32-unit chunk = 8 MMAs.  The weights of
+//     the i, f, o gates are stored halved (sigmoid(x) = 0.5 + 0.5 tanh(x / 2): the accumulator IS the tanh argument) and every
+//     x-piece carries one more K = 16 step whose first two rows are the bias as an fp16 pair (rounding + remainder); it is
+//     multiplied by a constant operand tile of ones, so the bias is added by the tensor pipe and the epilogue warps - the
+//     binding resource: XU pipe 60 %, issue slots 61 %, tensor pipe 44 % busy before this change - neither load nor add it;
 //   * accumulators: two 128-column TMEM slots, used alternately by the chunk sequence A0..A3, B0..B3, A0.. (one issuer warp
 //     per slot); h_A and h_B as packed fp16 pairs in TMEM (2 x 64 columns each, written with tcgen05.st), A operand of the
 //     recurrent MMAs ([a_tmem] form);
 //   * x1 (layer A's input: the previous layer's fp16 units, dropout mask ANDed in by the loader warps) and x2 = dropout(h_A)
 //     (written by the epilogue warps as they produce h_A; double-buffered by item parity) are shared-memory operand tiles;
-//   * the dropout keep-bits of x2 are drawn by the LOADER warps one wave ahead (Philox, or the injected bytes) and handed to
-//     the epilogue as one 32-bit word per (row, 8 units) in shared memory; the epilogue expands it with 4 PRMT (sign-replicate);
+//   * the dropout keep-bits of x2 are drawn by the LOADER warps a full wave ahead (Philox, or the injected bytes; three buffers)
+//     and handed to the epilogue as one 32-bit word per (row, 16 units) in shared memory; the epilogue expands it with 4 PRMT
+//     (sign-replicate);
 //   * the fp32 cell states (2 x 32 values per thread) live in a per-CTA 128 KB scratch that stays in L2, prefetched one
 //     half-pass ahead (as in ape_lstm_tcs.cu);
 //   * the inter-layer sequence never touches HBM.
@@ -55,24 +60,27 @@ static_assert(EPI_THREADS * REGS_EPI + LOAD_WARPS * 32 * REGS_LOAD + 128 * REGS_
 #define TCW_REG_DEC(n) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(n))
 constexpr int ROWS = 128;
 constexpr uint32_t KG_BYTES_B = 64 * 16;           // one k-group of a 64-column weight tile
-constexpr uint32_t PIECE_BYTES = KG * KG_BYTES_B;  // 16 KB: one operand half of one chunk = one ring slot
-constexpr uint32_t CHUNK_BYTES = 2 * PIECE_BYTES;  // x k-groups then h k-groups of one chunk (kgx = KG for layers >= 1)
-constexpr uint32_t LAYER_BYTES = NCHL * CHUNK_BYTES;   // one CTA's half of a layer
+constexpr uint32_t PIECE_H_BYTES = KG * KG_BYTES_B;        // 16 KB: the recurrent half of one chunk
+constexpr uint32_t PIECE_X_BYTES = (KG + 2) * KG_BYTES_B;  // 18 KB: the x half + the bias k-step (k-group KG: rows 0, 1 = fp16(b), b - fp16(b))
+constexpr uint32_t SLOT_BYTES = PIECE_X_BYTES;     // one ring slot
+constexpr uint32_t CHUNK_BYTES = PIECE_X_BYTES + PIECE_H_BYTES;
+constexpr uint32_t LAYER_BYTES = NCHL * CHUNK_BYTES;   // one CTA's half of a layer (ape_lstm_tcw_layer_bytes = 2 x this)
 constexpr uint32_t A_BYTES = KG * ROWS * 16;       // one operand tile (32 KB)
-constexpr uint32_t MASK_BYTES = KG * ROWS * 4;     // keep-bit words of one item
+constexpr uint32_t ONES_BYTES = 2 * ROWS * 16;     // the constant A tile of the bias k-step: k-group 0 = [1, 1, 0 x 6] per row, k-group 1 = 0
+constexpr int NMASK = 3;                           // keep-bit buffers (item i in buffer i % 3: drawn a full wave ahead)
+constexpr uint32_t MASK_BYTES = (KG / 2) * ROWS * 4;   // keep-bit words of one item: one word per (row, 2 k-groups)
 constexpr int NP = 6;                              // ring depth (slots)
-constexpr uint32_t BIAS_BYTES = 2 * 4 * H * 4;     // both layers' scaled bias
 constexpr int NFULL = 8;                           // "piece landed" barriers, indexed by piece number (> NP: never alias)
 constexpr uint32_t OUT_N = 32;                     // output product: 16 outputs x {fp16(W_o), W_o - fp16(W_o)}
 constexpr uint32_t OUT_BYTES = KG * (OUT_N / 2) * 16;   // this CTA's tile of it (4 KB)
 constexpr uint32_t BAR_BLOCK_BYTES = 512;
-constexpr uint32_t SMEM = A_BYTES + 2 * A_BYTES + 2 * MASK_BYTES + NP * PIECE_BYTES + BIAS_BYTES + BAR_BLOCK_BYTES;
+constexpr uint32_t SMEM = A_BYTES + 2 * A_BYTES + NMASK * MASK_BYTES + NP * SLOT_BYTES + ONES_BYTES + BAR_BLOCK_BYTES;
 constexpr uint32_t ACC_COLS = 256, HA_COL = 256, HB_COL = 384, H_COLS = H / 2, TMEM_COLS = 512;
 constexpr size_t CSTATE_FLOATS = (size_t)2 * H * ROWS;     // per CTA: [layer][k-group * 2 + half][row] float4
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 
 enum {
-    BAR_X1_READY = 0, BAR_X1_DONE = 1, BAR_MASK_READY = 2, BAR_ACC_READY = 4, BAR_SLOT_FREE = 6, BAR_HA_READY = 8,
+    BAR_X1_READY = 0, BAR_X1_DONE = 1, BAR_MASK_READY = 2, BAR_ACC_READY = 5, BAR_SLOT_FREE = 7, BAR_HA_READY = 9,
     BAR_HB_READY = BAR_HA_READY + NCHL, BAR_W_FULL = BAR_HB_READY + NCHL, BAR_W_EMPTY = BAR_W_FULL + NFULL,
     BAR_OUT_READY = BAR_W_EMPTY + NP, BAR_COUNT = BAR_OUT_READY + 1
 };
@@ -83,10 +91,12 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-// keep-bit word of 8 units: byte k (k = 0..3) carries unit k in bit 7 and unit 4+k in bit 6.  From the four half2 AND-masks:
-__device__ __forceinline__ uint32_t keep_word(const uint4 m) {
-    return (prmt(m.x, m.y, 0x6420u) & 0x80808080u) | (prmt(m.z, m.w, 0x6420u) & 0x40404040u);
+// keep-bit word of 8 units: byte k (k = 0..3) carries unit k in bit 7 and unit 4+k in bit 6.  From the four flag words of a
+// draw (unit 2i: bit 15 of word i, unit 2i+1: bit 31):
+__device__ __forceinline__ uint32_t keep_word(const uint4 f) {
+    return (prmt(f.x, f.y, 0x7531u) & 0x80808080u) | ((prmt(f.z, f.w, 0x7531u) >> 1) & 0x40404040u);
 }
+// a mask word serves two k-groups: the even one in bits 7 / 6 of every byte, the odd one in bits 5 / 4
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constant__ TcLayerArgs b) {
@@ -97,10 +107,10 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sX1 = smem;                                       // [A_BYTES] layer A's input tile of the current item
     uint8_t* sX2 = sX1 + A_BYTES;                              // [2][A_BYTES] dropout(h_A) of item i in buffer i & 1
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sX2 + 2 * A_BYTES);   // [2][KG][ROWS] keep-bit words of item i in buffer i & 1
-    uint8_t* sW = reinterpret_cast<uint8_t*>(sMask) + 2 * MASK_BYTES;   // [NP][PIECE_BYTES] weight ring
-    float* sBias = reinterpret_cast<float*>(sW + NP * PIECE_BYTES);     // [2][4H] column 4u+g, scaled for the tanh form
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * 4 * H);
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sX2 + 2 * A_BYTES);   // [NMASK][KG / 2][ROWS] keep-bit words of item i in buffer i % 3
+    uint8_t* sW = reinterpret_cast<uint8_t*>(sMask) + NMASK * MASK_BYTES;   // [NP][SLOT_BYTES] weight ring
+    uint8_t* sOnes = sW + NP * SLOT_BYTES;                     // [2][ROWS] units: the A operand of the bias k-step
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -111,7 +121,8 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
     const bool has_out = b.preds != nullptr;
 
     tc::timeline_stamp(a.timeline, 0);
-    for (int i = tid; i < 4 * H; i += THREADS) { sBias[i] = a.bias_s[i]; sBias[4 * H + i] = b.bias_s[i]; }
+    for (int i = tid; i < 2 * ROWS; i += THREADS)              // halfs 0, 1 of every row = 1.0: they meet the bias rows of the x-pieces
+        reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(i < ROWS ? 0x3C003C00u : 0u, 0u, 0u, 0u);
     if (warp == MMA_WARP) {
         tmem_alloc<2>(tmem_slot, TMEM_COLS);
         tmem_relinquish<2>();
@@ -119,8 +130,8 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
     if (tid == 0) {
         mbar_init(&bars[BAR_X1_READY], 2 * LOAD_WARPS);
         mbar_init(&bars[BAR_X1_DONE], N_ISSUERS);              // each issuer commits after ITS last x-part of layer A
+        for (int i = 0; i < NMASK; ++i) mbar_init(&bars[BAR_MASK_READY + i], LOAD_WARPS);   // CTA-local
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars[BAR_MASK_READY + i], LOAD_WARPS);  // CTA-local
             mbar_init(&bars[BAR_ACC_READY + i], 1);
             mbar_init(&bars[BAR_SLOT_FREE + i], 2 * EPI_WARPS);
         }
@@ -152,14 +163,14 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
         // them from the thread / CTA index in every half-pass, which had been a fifth of the epilogue's instructions)
         unsigned long long cst_base = reinterpret_cast<unsigned long long>(
             reinterpret_cast<float4*>(a.cstate + (size_t)blockIdx.x * CSTATE_FLOATS) + (size_t)(2 * s) * ROWS + row_l);
-        uint32_t bias_base = smem_u32(sBias + 32 * s);
         uint32_t acc0 = tmem + t_lane + (uint32_t)(32 * s);                          // this thread's accumulator columns of a slot
         uint32_t hst0 = tmem + t_lane + (uint32_t)(4 * s);                           // ... its 4 columns of an h buffer (+ 16 per chunk)
         uint32_t x2_base = smem_u32(sX2) + unit_offset(ROWS, row_l, s);              // ... its unit of an x2 tile (+ 4 k-groups per chunk)
-        uint32_t mask_base = smem_u32(sMask + (size_t)s * ROWS + row_l);
+        uint32_t mask_base = smem_u32(sMask + (size_t)(s >> 1) * ROWS + row_l);     // word (row, k-groups 4 cl + {0, 1} | {2, 3}) + 2 cl rows of words
+        const uint32_t mask_shift = 2u * (uint32_t)(s & 1);
         uint32_t bars_local = smem_u32(bars), bars_leader;                           // barrier blocks: own CTA's, the leader's (cluster address)
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bars_leader) : "r"(bars_local), "r"(0));
-        asm volatile("" : "+l"(cst_base), "+r"(bias_base), "+r"(acc0), "+r"(hst0), "+r"(x2_base), "+r"(mask_base), "+r"(bars_local), "+r"(bars_leader));
+        asm volatile("" : "+l"(cst_base), "+r"(acc0), "+r"(hst0), "+r"(x2_base), "+r"(mask_base), "+r"(bars_local), "+r"(bars_leader));
         float4* const cst0 = reinterpret_cast<float4*>(cst_base);
         auto arrive_leader = [&](int bar) {
             asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bars_leader + (uint32_t)bar * 8u) : "memory");
@@ -168,8 +179,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             uint32_t spins = 0;
             while (!mbar_try_wait_addr(bars_local + (uint32_t)bar * 8u, parity)) { if (++spins > MBAR_WD_SPINS) __trap(); }
         };
-        auto lds128 = [](uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; };
-        uint32_t ph_out = 0;
+        uint32_t ph_out = 0, mbuf = NMASK - 1, mph = 1;        // mask buffer / barrier phase of A's item: w % 3, (w / 3) & 1
         int tA = 0, tB = -1, tileB = cluster_id - n_clusters;  // advanced at the top of every wave
 
         for (int w = 0; w <= NI; ++w) {
@@ -177,8 +187,9 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             if (w > 0) { if (++tA == T) tA = 0; }
             if (B_on) { if (++tB == T) tB = 0; if (tB == 0) tileB += n_clusters; }
             const bool final_out = B_on && has_out && tB == T - 1;
-            const uint32_t bufA = (uint32_t)w & 1u;            // x2 / mask buffer of A's item
-            if (A_on) wait_bar(BAR_MASK_READY + (int)bufA, ((uint32_t)w >> 1) & 1u);
+            const uint32_t bufA = (uint32_t)w & 1u;            // x2 buffer of A's item
+            if (++mbuf == NMASK) { mbuf = 0; mph ^= 1u; }
+            if (A_on) wait_bar(BAR_MASK_READY + (int)mbuf, mph);
 
             const int hp_begin = A_on ? 0 : 2 * NCHL, hp_end = B_on ? 4 * NCHL : 2 * NCHL;
             // One set of 16 accumulator registers and ONE load site per half-pass: the second half of a chunk is requested as soon as
@@ -203,18 +214,11 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                 const int layer = hp >> 3, cl = (hp >> 1) & 3, half = hp & 1, slot = (hp >> 1) & 1;
                 const int t_cur = t_of(layer);
                 tmem_ld_wait();
-                // gate pre-activations in the tanh form: sigmoid(x) = 0.5 + 0.5 tanh(x / 2); bias stored as 0.5 b (i, f, o), b (g)
+                // the accumulators ARE the tanh arguments: sigmoid(x) = 0.5 + 0.5 tanh(x / 2) with the 0.5 folded into the weights
+                // of the i, f, o gates, and the bias added by the tensor pipe (the bias k-step of every x-piece)
                 float tg[16];
-                {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint4 bs = lds128(bias_base + (uint32_t)((layer * 4 * H + cl * 128 + half * 16 + 4 * u) * 4));
-                        tg[4 * u + 0] = fmaf(__uint_as_float(r[4 * u + 0]), 0.5f, __uint_as_float(bs.x));
-                        tg[4 * u + 1] = fmaf(__uint_as_float(r[4 * u + 1]), 0.5f, __uint_as_float(bs.y));
-                        tg[4 * u + 2] = __uint_as_float(r[4 * u + 2]) + __uint_as_float(bs.z);
-                        tg[4 * u + 3] = fmaf(__uint_as_float(r[4 * u + 3]), 0.5f, __uint_as_float(bs.w));
-                    }
-                }
+                for (int i = 0; i < 16; ++i) tg[i] = __uint_as_float(r[i]);
                 if (half == 1) {                               // chunk fully drained: its issuer may refill the slot
                     fence_before_sync();
                     __syncwarp();
@@ -224,8 +228,10 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                 if (hp + 1 < hp_end) cbuf[(hp + 1) & 1] = t_of((hp + 1) >> 3) > 0 ? __ldcg(cst_at(hp + 1)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 if (half == 0) tmem_ld_x16(acc0 + (uint32_t)(slot * 128 + 16), r);
                 uint32_t mw = 0;
-                if (layer == 0 && half == 1)
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mw) : "r"(mask_base + (bufA * KG + 4u * (uint32_t)cl) * (ROWS * 4)));
+                if (layer == 0 && half == 1) {
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mw) : "r"(mask_base + (mbuf * (KG / 2) + 2u * (uint32_t)cl) * (ROWS * 4)));
+                    mw <<= mask_shift;
+                }
 
                 // 5 MUFU per cell
 #pragma unroll
@@ -308,17 +314,17 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
         }
     } else if (warp < MMA_WARP) {
         TCW_REG_DEC(REGS_LOAD);
-        // =================================== loader warps: x1 of item i, keep-bit words of item i ============================
-        // Two threads per row, 8 k-groups each (with one thread per row - 32 Philox draws per item on a single warp per SM
-        // quarter - the keep-bit words arrived late and the epilogue warps spent a sixth of their time waiting for them).  Item i's
-        // x1 tile may be written once the x-parts of item i-1 have retired (X1_DONE); the loads and the Philox draws of the first
-        // batch are done before that wait.
+        // =================================== loader warps: keep-bit words of item i, then x1 of item i =======================
+        // Two threads per row, 8 k-groups each.  Per item: first the keep-bit words of gap B (what the epilogue needs at the top of
+        // wave i - drawn here a full wave ahead, into buffer i % 3), then the loads and Philox draws of x1; item i's x1 tile may be
+        // written once the x-parts of item i-1 have retired (X1_DONE).
         const int row_l = (tid - EPI_THREADS) & (ROWS - 1);
         const int j0 = ((tid - EPI_THREADS) >> 7) * (KG / 2);  // this thread's k-groups: j0 .. j0 + 7
         constexpr int BK = 2;                                  // k-groups per batch of loads (register budget of the loader warps)
         int t = -1, tile = cluster_id - n_clusters;
         int e = 0, smp = 0, bidx = 0, f = 0;
         bool valid = false;
+        uint32_t mbuf = NMASK - 1;
         for (int i = 0; i < NI; ++i) {
             if (++t == T) t = 0;
             if (t == 0) {
@@ -329,6 +335,36 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                 bidx = e / a.nF; f = stream_frame0(a.stream_frames, a.frame0, bidx) + e % a.nF;
             }
             const uint32_t stream = a.stream_id0 + (uint32_t)bidx;
+            // keep-bit words of gap B (between layers A and B) for item i.  Buffer i % 3 was last read by the epilogue during A's
+            // passes of item i-3, in wave i-3; this thread has seen X1_DONE(i-2), which fires in wave i-2.
+            if (++mbuf == NMASK) mbuf = 0;
+            uint32_t* mdst = sMask + (size_t)mbuf * (KG / 2) * ROWS + row_l;
+#pragma unroll 2
+            for (int m = j0 / 2; m < j0 / 2 + KG / 4; ++m) {
+                uint32_t wbits = 0xF0F0F0F0u;
+                if (b.mask_mode == APE_MASK_PHILOX) {
+                    const uint32_t w0 = keep_word(philox_keep_flags_rk(b.rk, stream, (uint32_t)f, (uint32_t)smp, (uint32_t)b.gap, (uint32_t)t, (uint32_t)(2 * m), b.keep_thr16));
+                    const uint32_t w1 = keep_word(philox_keep_flags_rk(b.rk, stream, (uint32_t)f, (uint32_t)smp, (uint32_t)b.gap, (uint32_t)t, (uint32_t)(2 * m + 1), b.keep_thr16));
+                    wbits = w0 | (w1 >> 2);
+                } else if (b.mask_mode == APE_MASK_INJECTED) {
+                    wbits = 0;
+                    if (valid) {
+                        const uint4 mm = __ldg(reinterpret_cast<const uint4*>(
+                            b.masks + ((((size_t)e * b.n_gaps + b.gap) * T + t) * b.n + smp) * H + m * 16));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            wbits |= ((mm.x >> (8 * k)) & 0xFFu) ? (0x80u << (8 * k)) : 0u;
+                            wbits |= ((mm.y >> (8 * k)) & 0xFFu) ? (0x40u << (8 * k)) : 0u;
+                            wbits |= ((mm.z >> (8 * k)) & 0xFFu) ? (0x20u << (8 * k)) : 0u;
+                            wbits |= ((mm.w >> (8 * k)) & 0xFFu) ? (0x10u << (8 * k)) : 0u;
+                        }
+                    }
+                }
+                mdst[(size_t)m * ROWS] = wbits;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[BAR_MASK_READY + mbuf]);
+
             const uint4* src = reinterpret_cast<const uint4*>(a.in);
             if (a.in_mode == tc::IN_UNITS) src += ((((size_t)tile * T + t) * 2 + rank) * KG) * ROWS + row_l;
             else src += ((((size_t)(e >> (a.in_rpc_shift + 1)) * T + t) * 2 + ((e >> a.in_rpc_shift) & 1)) * KG) * ROWS +
@@ -363,30 +399,6 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&bars[BAR_X1_READY], rank);
-            // keep-bit words of gap B (between layers A and B) for item i.  Buffer i & 1 was last read by the epilogue during A's
-            // passes of item i-2: those ended before X1_DONE(i-1), which this thread has seen.
-            uint32_t* mdst = sMask + (size_t)((uint32_t)i & 1u) * KG * ROWS + row_l;
-#pragma unroll 4
-            for (int j = j0; j < j0 + KG / 2; ++j) {
-                uint32_t wbits = 0xC0C0C0C0u;
-                if (b.mask_mode == APE_MASK_PHILOX) {
-                    wbits = keep_word(APE_PHILOX_DRAW(b, stream, (uint32_t)f, (uint32_t)smp, (uint32_t)b.gap, (uint32_t)t, (uint32_t)j, b.keep_thr16));
-                } else if (b.mask_mode == APE_MASK_INJECTED) {
-                    wbits = 0;
-                    if (valid) {
-                        const uint2 m = __ldg(reinterpret_cast<const uint2*>(
-                            b.masks + ((((size_t)e * b.n_gaps + b.gap) * T + t) * b.n + smp) * H + j * 8));
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            wbits |= ((m.x >> (8 * k)) & 0xFFu) ? (0x80u << (8 * k)) : 0u;
-                            wbits |= ((m.y >> (8 * k)) & 0xFFu) ? (0x40u << (8 * k)) : 0u;
-                        }
-                    }
-                }
-                mdst[(size_t)j * ROWS] = wbits;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[BAR_MASK_READY + (i & 1)]);
         }
     } else {
       TCW_REG_DEC(REGS_MMA);            // (issuers, ring producer and the idle warp that pads their warpgroup)
@@ -398,7 +410,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             const uint32_t my_slot = (uint32_t)(warp - MMA_WARP);
             const uint32_t idesc = make_idesc_f16(256, 128), idesc_out = make_idesc_f16(256, OUT_N);
             const uint64_t dX1 = make_desc(smem_u32(sX1), LBO_A, SBO), dX2 = make_desc(smem_u32(sX2), LBO_A, SBO);
-            const uint64_t dW = make_desc(smem_u32(sW), LBO_B, SBO);
+            const uint64_t dW = make_desc(smem_u32(sW), LBO_B, SBO), dOnes = make_desc(smem_u32(sOnes), LBO_A, SBO);
             const uint32_t bar_full = smem_u32(&bars[BAR_W_FULL]), bar_empty = smem_u32(&bars[BAR_W_EMPTY]);
             const uint32_t d_tmem = tmem + my_slot * 128u;
             uint32_t wslot = 0, gpiece = 0, uses = 0;
@@ -415,10 +427,11 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                 wait_full();
                 fence_after_sync();
                 if (elect_one()) {
-                    const uint64_t bd = dW + wslot * (PIECE_BYTES >> 4);
+                    const uint64_t bd = dW + wslot * (SLOT_BYTES >> 4);
                     mma_f16<2>(d_tmem, dx, bd, idesc, 0u);
 #pragma unroll
                     for (uint32_t m = 1; m < KG / 2; ++m) mma_f16<2>(d_tmem, dx + m * (2 * LBO_A >> 4), bd + m * (2 * LBO_B >> 4), idesc, 1u);
+                    mma_f16<2>(d_tmem, dOnes, bd + (KG / 2) * (2 * LBO_B >> 4), idesc, 1u);      // + bias (ones x the piece's bias rows)
                     commit_pair_addr(bar_empty + wslot * 8, 0x3);          // both CTAs' producers may refill this slot
                     if (t == 0) commit_pair(&bars[BAR_ACC_READY + my_slot], 0x3);
                     if (x1_layer && cl >= NCHL - 2) commit_pair(&bars[BAR_X1_DONE], 0x3);
@@ -429,7 +442,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                     wait_full();
                     fence_after_sync();
                     if (elect_one()) {
-                        const uint64_t bd = dW + wslot * (PIECE_BYTES >> 4);
+                        const uint64_t bd = dW + wslot * (SLOT_BYTES >> 4);
 #pragma unroll
                         for (uint32_t m = 0; m < KG / 2; ++m) mma_f16_ts<2>(d_tmem, h_tmem + 8 * m, bd + m * (2 * LBO_B >> 4), idesc, 1u);
                         commit_pair_addr(bar_empty + wslot * 8, 0x3);
@@ -446,7 +459,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                     wait_full();
                     fence_after_sync();
                     if (elect_one()) {
-                        const uint64_t bd = make_desc(smem_u32(sW) + wslot * PIECE_BYTES, (OUT_N / 2) * 16, SBO);
+                        const uint64_t bd = make_desc(smem_u32(sW) + wslot * SLOT_BYTES, (OUT_N / 2) * 16, SBO);
                         const uint32_t at = tmem + HB_COL + (uint32_t)(T & 1) * H_COLS, dt = tmem + HB_COL + (uint32_t)((T & 1) ^ 1) * H_COLS;
 #pragma unroll
                         for (uint32_t m = 0; m < KG / 2; ++m) mma_f16_ts<2>(dt, at + 8 * m, bd + m * (2 * (OUT_N / 2) * 16 >> 4), idesc_out, m > 0 ? 1u : 0u);
@@ -509,15 +522,15 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
         }
       } else if (warp == TMA_WARP && lane == 0) {
         // =================================== weight-ring producer (one lane per CTA) =====================================
-        const uint8_t* WA = a.W + (size_t)rank * LAYER_BYTES;  // this CTA's half of each layer's weight tiles
-        const uint8_t* WB = b.W + (size_t)rank * LAYER_BYTES;
+        const uint8_t* WA = a.Ww + (size_t)rank * LAYER_BYTES;  // this CTA's half of each layer's pieces
+        const uint8_t* WB = b.Ww + (size_t)rank * LAYER_BYTES;
         uint32_t wslot = 0, wphase = 0, gpiece = 0;
         bool wrapped = false;
         auto put = [&](const uint8_t* src, uint32_t bytes) {
             uint64_t* full = &bars[BAR_W_FULL + (gpiece & (NFULL - 1))];
             if (wrapped) mbar_wait_wd(&bars[BAR_W_EMPTY + wslot], wphase ^ 1);   // previous occupant consumed
             mbar_arrive_expect_tx(full, bytes);
-            bulk_g2s(sW + wslot * PIECE_BYTES, src, bytes, full);
+            bulk_g2s(sW + wslot * SLOT_BYTES, src, bytes, full);
             if (++wslot == NP) { wslot = 0; wphase ^= 1; wrapped = true; }
             ++gpiece;
         };
@@ -528,12 +541,12 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             if (B_on) { if (++tB == T) tB = 0; }
             if (A_on) for (int cl = 0; cl < NCHL; ++cl) {
                 if (cl == 2 && has_out && w >= 2 && tB == 0) put(b.Wo16 + (size_t)rank * OUT_BYTES, OUT_BYTES);
-                put(WA + (size_t)cl * CHUNK_BYTES, PIECE_BYTES);
-                if (tA > 0) put(WA + (size_t)cl * CHUNK_BYTES + PIECE_BYTES, PIECE_BYTES);
+                put(WA + (size_t)cl * CHUNK_BYTES, PIECE_X_BYTES);
+                if (tA > 0) put(WA + (size_t)cl * CHUNK_BYTES + PIECE_X_BYTES, PIECE_H_BYTES);
             }
             if (B_on) for (int cl = 0; cl < NCHL; ++cl) {
-                put(WB + (size_t)cl * CHUNK_BYTES, PIECE_BYTES);
-                if (tB > 0) put(WB + (size_t)cl * CHUNK_BYTES + PIECE_BYTES, PIECE_BYTES);
+                put(WB + (size_t)cl * CHUNK_BYTES, PIECE_X_BYTES);
+                if (tB > 0) put(WB + (size_t)cl * CHUNK_BYTES + PIECE_X_BYTES, PIECE_H_BYTES);
             }
         }
         if (has_out) put(b.Wo16 + (size_t)rank * OUT_BYTES, OUT_BYTES);
@@ -548,11 +561,13 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
 
 bool supported(int Hh, int T, int O) { return Hh == H && T >= 2 && O <= (int)OUT_N / 2; }
 
+size_t layer_bytes(int Hh) { return Hh == H ? (size_t)2 * LAYER_BYTES : 0; }
+
 size_t scratch_bytes(int Hh, int sm_count) { return Hh == H ? (size_t)sm_count * CSTATE_FLOATS * sizeof(float) : 0; }
 
 // layers A = a, B = b of one launch; a.cstate: scratch_bytes() bytes
 int launch_pair(const TcLayerArgs& a, const TcLayerArgs& b, int sm_count, cudaStream_t st) {
-    if (a.kgx != KG || b.kgx != KG || a.rpc != ROWS || !a.cstate || a.T != b.T || a.T < 2) return APE_ERR_UNSUPPORTED;
+    if (a.kgx != KG || b.kgx != KG || a.rpc != ROWS || !a.cstate || a.T != b.T || a.T < 2 || !a.Ww || !b.Ww) return APE_ERR_UNSUPPORTED;
     if (a.in_mode != tc::IN_UNITS && a.in_mode != tc::IN_SHARED_UNITS) return APE_ERR_UNSUPPORTED;
     if (b.preds && (!b.Wo16 || b.O > (int)OUT_N / 2)) return APE_ERR_UNSUPPORTED;
     APE_CUDA_TRY(cudaFuncSetAttribute(lstm_pair_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));

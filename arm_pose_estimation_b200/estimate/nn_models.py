@@ -93,6 +93,32 @@ def pack_lstm_weights_tc(state):
     w_lo = (w_full - w_hi.astype(np.float32)).astype(np.float16)
     for w in (w_hi, w_lo):
         parts.append(np.ascontiguousarray(w.reshape(n_cols, H // 8, 8).transpose(1, 0, 2)).view(np.uint8).ravel())
+    # The two-layer wavefront kernel (csrc/ape_lstm_tcw.cu; H = 128, L >= 3) streams the layers >= 1 as ring pieces: per CTA and
+    # chunk an x-piece [16 + 2 k-groups][64][8] and an h-piece [16][64][8].  The i, f, o columns are halved (exact in fp16 but for
+    # subnormals) so the accumulator is the tanh argument of sigmoid(x) = 0.5 + 0.5 tanh(x / 2); the x-piece's extra K = 16 step
+    # holds the scaled bias as an fp16 pair (rounding, remainder) in its rows 0 and 1 - the kernel multiplies it by a tile of ones.
+    if H == 128 and L >= 3:
+        half = np.float16(0.5)
+        for l in range(1, L):
+            w_ih, w_hh = st[f"lstm.weight_ih_l{l}"], st[f"lstm.weight_hh_l{l}"]
+            bias = st[f"lstm.bias_ih_l{l}"] + st[f"lstm.bias_hh_l{l}"]
+            for r in range(2):
+                n = 64 * r + nl
+                halved = (n % 4) != 2                                       # gate order i, f, g, o: all but g
+                for c in range(H // 32):
+                    rows = (n % 4) * H + 32 * c + n // 4
+                    b_s = np.where(halved, np.float32(0.5), np.float32(1.0)) * bias[rows]
+                    b_hi = b_s.astype(np.float16)
+                    b_lo = (b_s - b_hi.astype(np.float32)).astype(np.float16)
+                    for w, with_bias in ((w_ih, True), (w_hh, False)):
+                        t = w[rows].astype(np.float16)
+                        t[halved] = t[halved] * half
+                        if with_bias:
+                            ext = np.zeros((64, 16), np.float16)
+                            ext[:, 0], ext[:, 1] = b_hi, b_lo
+                            t = np.concatenate([t, ext], axis=1)
+                        kp = t.shape[1]
+                        parts.append(np.ascontiguousarray(t.reshape(64, kp // 8, 8).transpose(1, 0, 2)).view(np.uint8).ravel())
     return np.ascontiguousarray(np.concatenate(parts))
 
 
