@@ -48,10 +48,24 @@ using tc::tanh_approx;
 constexpr int H = 128, NCHL = H / 32, KG = H / 8;  // chunks per layer, k-groups per operand
 constexpr int EPI_WARPS = 16, LOAD_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS;   // leader CTA: two MMA issuers (issuer k owns accumulator slot k);
-constexpr int N_ISSUERS = 2;                       //   peer CTA: the first of them forwards "piece landed" to the leader
-constexpr int TMA_WARP = MMA_WARP + N_ISSUERS;     // one lane per CTA fills the weight ring
-constexpr int THREADS = (TMA_WARP + 2) * 32;       // 896 = 7 warpgroups (one idle warp pads the last one: setmaxnreg works per warpgroup)
+constexpr int N_ISSUERS = 2;                       // leader CTA: two MMA issuers (issuer k owns accumulator slot k); peer CTA: the first forwards "piece landed"
+constexpr int THREADS = (EPI_WARPS + LOAD_WARPS + 4) * 32;   // 896 = 7 warpgroups (one idle warp pads the issuers' one: setmaxnreg works per warpgroup)
+// Which warps play which role.  The warp scheduler prefers the higher warp id among eligible warps, and the epilogue warps are
+// the ones the wave waits for: APE_TCW_EPI_HIGH = 1 gives them the highest ids (issuers + ring producer 0..3, loaders 4..11,
+// epilogue 12..27); 0 is the first layout (epilogue 0..15, loaders 16..23, issuers 24..25, producer 26).
+#ifndef APE_TCW_EPI_HIGH
+#define APE_TCW_EPI_HIGH 1
+#endif
+#if APE_TCW_EPI_HIGH
+constexpr int MMA_WARP = 0, TMA_WARP = 2, LOAD_WARP0 = 4, EPI_WARP0 = 12;
+#else
+constexpr int EPI_WARP0 = 0, LOAD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + LOAD_WARPS, TMA_WARP = MMA_WARP + N_ISSUERS;
+#endif
+static_assert(EPI_WARP0 % 4 == 0 && LOAD_WARP0 % 4 == 0 && MMA_WARP % 4 == 0, "roles start on warpgroup boundaries (TMEM lane quarter = warp % 4)");
+// failed barrier probes of the epilogue warps back off for this long (0: re-probe at once; the probe itself suspends for a few dozen cycles)
+#ifndef APE_TCW_BACKOFF_NS
+#define APE_TCW_BACKOFF_NS 0
+#endif
 // Register file re-balanced per role (launch allocation 72 x 896): the epilogue's working set (accumulator columns, gate values,
 // prefetched cell state) spilled ~20 values per half-pass at 80 registers
 constexpr int REGS_EPI = 96, REGS_LOAD = 40, REGS_MMA = 40;
@@ -69,7 +83,10 @@ constexpr uint32_t A_BYTES = KG * ROWS * 16;       // one operand tile (32 KB)
 constexpr uint32_t ONES_BYTES = 2 * ROWS * 16;     // the constant A tile of the bias k-step: k-group 0 = [1, 1, 0 x 6] per row, k-group 1 = 0
 constexpr int NMASK = 3;                           // keep-bit buffers (item i in buffer i % 3: drawn a full wave ahead)
 constexpr uint32_t MASK_BYTES = (KG / 2) * ROWS * 4;   // keep-bit words of one item: one word per (row, 2 k-groups)
-constexpr int NP = 6;                              // ring depth (slots)
+#ifndef APE_TCW_NP
+#define APE_TCW_NP 6
+#endif
+constexpr int NP = APE_TCW_NP;                              // ring depth (slots)
 constexpr int NFULL = 8;                           // "piece landed" barriers, indexed by piece number (> NP: never alias)
 constexpr uint32_t OUT_N = 32;                     // output product: 16 outputs x {fp16(W_o), W_o - fp16(W_o)}
 constexpr uint32_t OUT_BYTES = KG * (OUT_N / 2) * 16;   // this CTA's tile of it (4 KB)
@@ -85,6 +102,29 @@ enum {
     BAR_OUT_READY = BAR_W_EMPTY + NP, BAR_COUNT = BAR_OUT_READY + 1
 };
 static_assert(BAR_COUNT * 8 + 16 <= BAR_BLOCK_BYTES, "barrier block too small");
+
+// Barrier waits of the warps that are NOT the bottleneck (loaders, issuers, ring producer / forwarder): a failed probe - it already
+// suspends the warp for a few dozen cycles - is followed by a nanosleep, because a polling warp re-issues ~7 instructions per
+// probe on the issue port it shares with the epilogue warps of its SM quarter.
+#ifndef APE_TCW_EARLY_FREE
+#define APE_TCW_EARLY_FREE 0
+#endif
+#ifndef APE_TCW_BO_LOAD
+#define APE_TCW_BO_LOAD 0
+#endif
+#ifndef APE_TCW_BO_MMA
+#define APE_TCW_BO_MMA 0
+#endif
+#ifndef APE_TCW_BO_RING
+#define APE_TCW_BO_RING 0
+#endif
+template <int NS> __device__ __forceinline__ void mbar_wait_bo(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!umma::mbar_try_wait(bar, parity)) {
+        if (++spins > umma::MBAR_WD_SPINS) __trap();
+        if (NS > 0) __nanosleep(NS);
+    }
+}
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
@@ -151,11 +191,11 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
     const uint32_t tmem = *tmem_slot;
     tc::timeline_stamp(a.timeline, 1);
 
-    if (warp < EPI_WARPS) {
+    if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
         TCW_REG_INC(REGS_EPI);
         // =================================== epilogue warps ===========================================================
         // warp (q, s): rows 32q..32q+31 (its TMEM lane quarter) x the 8 hidden units 8s..8s+7 of EVERY 32-unit chunk of both layers.
-        const int q = warp & 3, s = warp >> 2;
+        const int q = warp & 3, s = (warp - EPI_WARP0) >> 2;
         const int row_l = 32 * q + lane;
         const uint32_t t_lane = (uint32_t)(32 * q) << 16;
         // everything a half-pass addresses is (one per-thread base) + (a compile-time offset):
@@ -177,9 +217,19 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
         };
         auto wait_bar = [&](int bar, uint32_t parity) {        // spin with the watchdog (a protocol bug traps instead of hanging)
             uint32_t spins = 0;
-            while (!mbar_try_wait_addr(bars_local + (uint32_t)bar * 8u, parity)) { if (++spins > MBAR_WD_SPINS) __trap(); }
+            while (!mbar_try_wait_addr(bars_local + (uint32_t)bar * 8u, parity)) {
+                if (++spins > MBAR_WD_SPINS) __trap();
+#if APE_TCW_BACKOFF_NS > 0
+                __nanosleep(APE_TCW_BACKOFF_NS);
+#endif
+            }
         };
         uint32_t ph_out = 0, mbuf = NMASK - 1, mph = 1;        // mask buffer / barrier phase of A's item: w % 3, (w / 3) & 1
+        // (the loop bound is re-derived here from an opaque copy of the parameter: carried over from the common prologue - compiled
+        // for the 72-register launch allocation - it lived in a local-memory slot that every wave re-read through a 28 KB L1)
+        int npt = a.n_pair_tiles;
+        asm volatile("" : "+r"(npt));
+        const int NI = ((npt - cluster_id + n_clusters - 1) / n_clusters) * T;
         int tA = 0, tB = -1, tileB = cluster_id - n_clusters;  // advanced at the top of every wave
 
         for (int w = 0; w <= NI; ++w) {
@@ -219,11 +269,13 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                 float tg[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) tg[i] = __uint_as_float(r[i]);
+#if !APE_TCW_EARLY_FREE
                 if (half == 1) {                               // chunk fully drained: its issuer may refill the slot
                     fence_before_sync();
                     __syncwarp();
                     if (lane == 0) arrive_leader(BAR_SLOT_FREE + slot);
                 }
+#endif
                 const float cp[4] = {cbuf[hp & 1].x, cbuf[hp & 1].y, cbuf[hp & 1].z, cbuf[hp & 1].w};
                 if (hp + 1 < hp_end) cbuf[(hp + 1) & 1] = t_of((hp + 1) >> 3) > 0 ? __ldcg(cst_at(hp + 1)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 if (half == 0) tmem_ld_x16(acc0 + (uint32_t)(slot * 128 + 16), r);
@@ -236,6 +288,17 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                 // 5 MUFU per cell
 #pragma unroll
                 for (int i = 0; i < 16; ++i) tg[i] = tanh_approx(tg[i]);
+#if APE_TCW_EARLY_FREE
+                if (half == 0) {
+                    // The chunk's second half was requested above and has had the 16 tanh issues to arrive: with it in registers the
+                    // chunk is drained and its issuer may refill the slot - most of a half-pass earlier than when the second
+                    // half-pass starts (the refill's issue -> commit -> wake-up chain is what the step waits for).
+                    tmem_ld_wait();
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) arrive_leader(BAR_SLOT_FREE + slot);
+                }
+#endif
                 float hv[4], cn[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -312,14 +375,14 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                 fence_before_sync();
             }
         }
-    } else if (warp < MMA_WARP) {
+    } else if (warp >= LOAD_WARP0 && warp < LOAD_WARP0 + LOAD_WARPS) {
         TCW_REG_DEC(REGS_LOAD);
         // =================================== loader warps: keep-bit words of item i, then x1 of item i =======================
         // Two threads per row, 8 k-groups each.  Per item: first the keep-bit words of gap B (what the epilogue needs at the top of
         // wave i - drawn here a full wave ahead, into buffer i % 3), then the loads and Philox draws of x1; item i's x1 tile may be
         // written once the x-parts of item i-1 have retired (X1_DONE).
-        const int row_l = (tid - EPI_THREADS) & (ROWS - 1);
-        const int j0 = ((tid - EPI_THREADS) >> 7) * (KG / 2);  // this thread's k-groups: j0 .. j0 + 7
+        const int row_l = (tid - LOAD_WARP0 * 32) & (ROWS - 1);
+        const int j0 = ((tid - LOAD_WARP0 * 32) >> 7) * (KG / 2);  // this thread's k-groups: j0 .. j0 + 7
         constexpr int BK = 2;                                  // k-groups per batch of loads (register budget of the loader warps)
         int t = -1, tile = cluster_id - n_clusters;
         int e = 0, smp = 0, bidx = 0, f = 0;
@@ -392,7 +455,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                         pre[jj].w &= ((m.y & 0xFF0000u) ? 0xFFFFu : 0u) | ((m.y & 0xFF000000u) ? 0xFFFF0000u : 0u);
                     }
                 }
-                if (b0 == j0 && i >= 1) mbar_wait_wd(&bars[BAR_X1_DONE], ((uint32_t)(i - 1)) & 1u);
+                if (b0 == j0 && i >= 1) mbar_wait_bo<APE_TCW_BO_LOAD>(&bars[BAR_X1_DONE], ((uint32_t)(i - 1)) & 1u);
 #pragma unroll
                 for (int jj = 0; jj < BK; ++jj) *reinterpret_cast<uint4*>(sX1 + unit_offset(ROWS, row_l, b0 + jj)) = pre[jj];
             }
@@ -402,7 +465,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
         }
     } else {
       TCW_REG_DEC(REGS_MMA);            // (issuers, ring producer and the idle warp that pads their warpgroup)
-      if (warp < TMA_WARP) {
+      if (warp >= MMA_WARP && warp < MMA_WARP + N_ISSUERS) {
         if (rank == 0) {
             // =============================== MMA issuers (leader CTA; the whole warp runs, one elected lane issues) =====
             // Issuer k owns accumulator slot k, i.e. chunks 1, 3 (k = 1) or 0, 2 (k = 0) of every layer group.  Both walk the whole
@@ -417,12 +480,15 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             auto ring_next = [&]() { wslot = wslot + 1 == NP ? 0 : wslot + 1; ++gpiece; };
             auto wait_full = [&]() {
                 uint32_t spins = 0;
-                while (!mbar_try_wait_addr(bar_full + (gpiece & (NFULL - 1)) * 8, (gpiece / NFULL) & 1)) { if (++spins > MBAR_WD_SPINS) __trap(); }
+                while (!mbar_try_wait_addr(bar_full + (gpiece & (NFULL - 1)) * 8, (gpiece / NFULL) & 1)) {
+                    if (++spins > MBAR_WD_SPINS) __trap();
+                    if (APE_TCW_BO_MMA > 0) __nanosleep(APE_TCW_BO_MMA);
+                }
             };
             // one chunk of one layer: x-part from the shared-memory tile `dx`, recurrent part (t > 0) from the TMEM buffer `h_tmem`
             auto chunk = [&](int cl, bool mine, int t, uint64_t dx, uint32_t h_tmem, bool x1_layer) {
                 if (!mine) { ring_next(); if (t > 0) ring_next(); return; }
-                if (uses >= 1) mbar_wait_wd(&bars[BAR_SLOT_FREE + my_slot], (uses & 1) ^ 1);   // the epilogue drained the previous occupant
+                if (uses >= 1) mbar_wait_bo<APE_TCW_BO_MMA>(&bars[BAR_SLOT_FREE + my_slot], (uses & 1) ^ 1);   // the epilogue drained the previous occupant
                 ++uses;
                 wait_full();
                 fence_after_sync();
@@ -455,7 +521,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             // output layer of a finished tile: h_T (TMEM, B's buffer T & 1) x [fp16(W_o) | W_o - fp16(W_o)]^T into B's other h buffer
             auto out_piece = [&](uint32_t item_parity) {
                 if (my_slot == 0) {
-                    mbar_wait_wd(&bars[BAR_HB_READY + NCHL - 1], item_parity);     // all of h_T (slices are published in order)
+                    mbar_wait_bo<APE_TCW_BO_MMA>(&bars[BAR_HB_READY + NCHL - 1], item_parity);     // all of h_T (slices are published in order)
                     wait_full();
                     fence_after_sync();
                     if (elect_one()) {
@@ -477,9 +543,9 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                 if (B_on) { if (++tB == T) tB = 0; }
                 // h_A of item w-1 (A's recurrent operand, and B's input x2 of item w-1) is complete.  Waited for here, at the top of the
                 // wave, by both issuers: the barrier cannot run a second phase ahead, because item w's chunks are issued below.
-                if (w >= 1) mbar_wait_wd(&bars[BAR_HA_READY + NCHL - 1], ((uint32_t)(w - 1)) & 1u);
+                if (w >= 1) mbar_wait_bo<APE_TCW_BO_MMA>(&bars[BAR_HA_READY + NCHL - 1], ((uint32_t)(w - 1)) & 1u);
                 if (A_on) {
-                    mbar_wait_wd(&bars[BAR_X1_READY], (uint32_t)w & 1u);
+                    mbar_wait_bo<APE_TCW_BO_MMA>(&bars[BAR_X1_READY], (uint32_t)w & 1u);
                     fence_after_sync();
                     const uint32_t hA = tmem + HA_COL + (uint32_t)(tA & 1) * H_COLS;
 #pragma unroll
@@ -489,7 +555,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                     }
                 }
                 if (B_on) {
-                    if (w >= 2) mbar_wait_wd(&bars[BAR_HB_READY + NCHL - 1], ((uint32_t)(w - 2)) & 1u);   // h_B of item w-2
+                    if (w >= 2) mbar_wait_bo<APE_TCW_BO_MMA>(&bars[BAR_HB_READY + NCHL - 1], ((uint32_t)(w - 2)) & 1u);   // h_B of item w-2
                     fence_after_sync();
                     const uint64_t dx = dX2 + (((uint32_t)(w - 1)) & 1u) * (A_BYTES >> 4);
                     const uint32_t hB = tmem + HB_COL + (uint32_t)(tB & 1) * H_COLS;
@@ -502,7 +568,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
             // =============================== peer CTA: forward "piece landed in my ring" to the leader ==================
             uint32_t gpiece = 0;
             auto forward = [&]() {
-                mbar_wait_wd(&bars[BAR_W_FULL + (gpiece & (NFULL - 1))], (gpiece / NFULL) & 1);
+                mbar_wait_bo<APE_TCW_BO_RING>(&bars[BAR_W_FULL + (gpiece & (NFULL - 1))], (gpiece / NFULL) & 1);
                 mbar_arrive_remote(&bars[BAR_W_FULL + (gpiece & (NFULL - 1))], 0);
                 ++gpiece;
             };
@@ -528,7 +594,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
         bool wrapped = false;
         auto put = [&](const uint8_t* src, uint32_t bytes) {
             uint64_t* full = &bars[BAR_W_FULL + (gpiece & (NFULL - 1))];
-            if (wrapped) mbar_wait_wd(&bars[BAR_W_EMPTY + wslot], wphase ^ 1);   // previous occupant consumed
+            if (wrapped) mbar_wait_bo<APE_TCW_BO_RING>(&bars[BAR_W_EMPTY + wslot], wphase ^ 1);   // previous occupant consumed
             mbar_arrive_expect_tx(full, bytes);
             bulk_g2s(sW + wslot * SLOT_BYTES, src, bytes, full);
             if (++wslot == NP) { wslot = 0; wphase ^= 1; wrapped = true; }
