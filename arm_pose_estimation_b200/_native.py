@@ -25,8 +25,10 @@ SYMBOLS = (
     "ape_abi_version", "ape_last_cuda_error", "ape_device_info", "ape_lstm_blob_floats", "ape_features", "ape_features_push",
     "ape_mc_lstm_workspace_bytes", "ape_mc_lstm_fma", "ape_mc_lstm_tc_supported", "ape_lstm_tc_blob_bytes",
     "ape_mc_lstm_tc_workspace_bytes", "ape_mc_lstm_tc_workspace_bytes_all_steps", "ape_mc_lstm_tc", "ape_mc_lstm_tc_launch_count", "ape_philox_masks", "ape_ff_blob_floats", "ape_mc_ff", "ape_dense_act", "ape_fk_reduce", "ape_msg_from_est",
+    "ape_pipeline_create", "ape_pipeline_destroy", "ape_pipeline_submit", "ape_pipeline_wait", "ape_pipeline_query", "ape_pipeline_sync",
+    "ape_pipeline_fence",
     "ape_selfcheck_philox", "ape_selfcheck_keep8", "ape_selfcheck_features", "ape_selfcheck_row_pose", "ape_selfcheck_tcs_schedule",
-    "ape_selftest_umma",
+    "ape_selftest_umma", "ape_selftest_ffma_peak",
 )
 
 
@@ -59,6 +61,34 @@ class LstmArgs(C.Structure):
         ("tc_flags", C.c_int),
         ("h0", C.c_void_p),
         ("c0", C.c_void_p),
+    ]
+
+
+PIPELINE_MAX_SLOTS = 8
+PIPE_INPUT_PENDING, PIPE_CALLER_WAITS, PIPE_D2H = 1, 2, 4
+
+
+class PipelineDesc(C.Structure):
+    """``struct ape_pipeline_desc`` (include/ape_b200.h)."""
+    _fields_ = [
+        ("layout", C.c_int), ("kind", C.c_int), ("normalize", C.c_int), ("ncols", C.c_int),
+        ("xx_m", C.c_void_p),
+        ("xx_s", C.c_void_p),
+        ("raw", C.c_void_p),
+        ("feats", C.c_void_p),
+        ("feat_ring", C.c_int),
+        ("lstm", LstmArgs),
+        ("lane_workspace", C.c_void_p * 2),
+        ("yy_m", C.c_void_p),
+        ("yy_s", C.c_void_p),
+        ("body9", C.c_void_p),
+        ("target", C.c_int), ("smooth", C.c_int), ("emit_samples", C.c_int),
+        ("B", C.c_int), ("nF_max", C.c_int), ("n_slots", C.c_int),
+        ("out_dev", C.c_void_p * PIPELINE_MAX_SLOTS),
+        ("raw_host", C.c_void_p * PIPELINE_MAX_SLOTS),
+        ("out_host", C.c_void_p * PIPELINE_MAX_SLOTS),
+        ("frames_dev", C.c_void_p * 4),
+        ("frames_host", C.c_void_p * PIPELINE_MAX_SLOTS),
     ]
 
 
@@ -120,6 +150,20 @@ def load():
     lib.ape_fk_reduce.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.ape_msg_from_est.restype = i32
     lib.ape_msg_from_est.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp]
+    lib.ape_pipeline_create.restype = i32
+    lib.ape_pipeline_create.argtypes = [C.POINTER(PipelineDesc), C.POINTER(vp)]
+    lib.ape_pipeline_destroy.restype = i32
+    lib.ape_pipeline_destroy.argtypes = [vp]
+    lib.ape_pipeline_submit.restype = i32
+    lib.ape_pipeline_submit.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp, C.POINTER(i32)]
+    lib.ape_pipeline_wait.restype = i32
+    lib.ape_pipeline_wait.argtypes = [vp, i32]
+    lib.ape_pipeline_query.restype = i32
+    lib.ape_pipeline_query.argtypes = [vp, i32, C.POINTER(i32)]
+    lib.ape_pipeline_sync.restype = i32
+    lib.ape_pipeline_sync.argtypes = [vp]
+    lib.ape_pipeline_fence.restype = i32
+    lib.ape_pipeline_fence.argtypes = [vp, vp]
     # host self-check hooks: used by tests/ only
     lib.ape_selfcheck_philox.restype = i32
     lib.ape_selfcheck_philox.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
@@ -133,6 +177,8 @@ def load():
     lib.ape_selfcheck_tcs_schedule.argtypes = [i32, i32, C.POINTER(u32), i32, C.POINTER(i32)]
     lib.ape_selftest_umma.restype = i32
     lib.ape_selftest_umma.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    lib.ape_selftest_ffma_peak.restype = i32
+    lib.ape_selftest_ffma_peak.argtypes = [vp, i32, i32, C.POINTER(f32), vp]
     _lib = lib
     return lib
 

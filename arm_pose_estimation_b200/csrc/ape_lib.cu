@@ -6,7 +6,7 @@ namespace ape {
 thread_local cudaError_t g_last_err = cudaSuccess;
 }
 
-extern "C" int ape_abi_version(void) { return 5; }
+extern "C" int ape_abi_version(void) { return 6; }
 
 extern "C" const char* ape_last_cuda_error(void) { return cudaGetErrorString(ape::g_last_err); }
 

@@ -85,28 +85,37 @@ class EstimateBatch:
 
 
 class PendingEstimate:
-    """Handle of an enqueued ``BatchedEstimator.submit``: ``result()`` waits for its D2H copy and returns host arrays."""
+    """Handle of an enqueued ``BatchedEstimator.submit``: ``result()`` waits for its D2H copy and returns host arrays.
+    ``event`` is the torch event of the copy, or ``None`` when the call went through the native pipeline (``ape_pipeline_wait``)."""
 
     def __init__(self, owner, slot, nF, frame0, event):
         self.owner, self.slot, self.nF, self.frame0, self.event = owner, slot, nF, frame0, event
 
     def done(self):
-        return self.event.query()
+        if self.event is not None:
+            return self.event.query()
+        landed = ctypes.c_int(0)
+        N.check(self.owner.lib.ape_pipeline_query(self.owner._pipe, self.slot, ctypes.byref(landed)), "ape_pipeline_query")
+        return bool(landed.value)
 
     def result(self):
-        self.event.synchronize()
+        if self.event is not None:
+            self.event.synchronize()
+        else:
+            N.check(self.owner.lib.ape_pipeline_wait(self.owner._pipe, self.slot), "ape_pipeline_wait")
         msg, std, samples, status = self.owner._host_views(self.slot, self.nF)
         return EstimateBatch(msg, std, samples, status, self.frame0)
 
 
 class BatchedEstimator:
-    N_SLOTS = 6      # staging / result buffer sets: up to N_SLOTS - 1 submitted calls may be outstanding while the next is staged
+    N_SLOTS = int(os.environ.get("APE_N_SLOTS", "8"))      # staging / result buffer sets: up to N_SLOTS - 1 submitted calls may be outstanding while the next is staged
                      # (measured end to end, uarm 1024 x 100: 3 outstanding 0.413 ms/step, 5 outstanding 0.392, 7 outstanding 0.391)
 
     def __init__(self, kind, layout, state, seq_len, y_targets, stats, n_streams, mc_samples,
                  smooth=1, dropout=0.2, bonemap=None, frames_per_call=1, emit_samples=True, normalize=True,
                  mask_mode=N.MASK_PHILOX, philox_seed=0, first_stream=0, device=None,
-                 lstm_variant="auto", tc_min_rows=1, tc_tolerance_m=5e-5, pipeline=True, lanes=True, tc_flags=None):
+                 lstm_variant="auto", tc_min_rows=1, tc_tolerance_m=5e-5, pipeline=True, lanes=True, tc_flags=None,
+                 native_pipeline=None):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedEstimator needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = N.load()
@@ -204,9 +213,76 @@ class BatchedEstimator:
             self.lane_ws = [self.workspace, torch.empty_like(self.workspace)] if self.lanes else None
             self.l1_done = [None] * 4             # completion of the last call that used buffer set (call & 3)
             self.lstm_done = None             # last LSTM layer of the previous call (its predictions feed this call's smoothing window)
+            # The same pipeline as ONE C call per batch (csrc/ape_pipeline.cu: ape_pipeline_submit): used for every call that needs
+            # nothing call-specific from Python (no injected masks, no profiling / trace leg, no caller-owned frame counters).  The
+            # Python-level pipeline below remains for those, and as the A/B switch (native_pipeline=False | APE_NATIVE_PIPELINE=0).
+            if native_pipeline is None:
+                native_pipeline = os.environ.get("APE_NATIVE_PIPELINE", "1") != "0"
+            self._pipe = None
+            self._pipe_busy = False
+            self._py_dirty = False            # a Python-path call has run since the native pipeline last drained
+            self._launch_cache = {}
+            if native_pipeline and self.lanes and self.mask_mode != N.MASK_INJECTED and normalize:
+                self._make_native_pipeline()
         self.calls = 0
         self.frame = 0
         self.launches = 0             # kernels launched so far (bench.py reports it)
+
+    def _make_native_pipeline(self):
+        d = N.PipelineDesc()
+        d.layout, d.kind, d.normalize, d.ncols = self.layout, self.kind, 1 if self.normalize else 0, self.ncols
+        d.xx_m, d.xx_s = self.xx_m.data_ptr(), self.xx_s.data_ptr()
+        d.raw, d.feats, d.feat_ring = self.raw.data_ptr(), self.feats.data_ptr(), self.feat_ring
+        d.lstm = self._lstm_args(self.nF_max, 0, None, None)[0]
+        d.lane_workspace[0], d.lane_workspace[1] = self.lane_ws[0].data_ptr(), self.lane_ws[1].data_ptr()
+        d.yy_m, d.yy_s, d.body9 = self.yy_m.data_ptr(), self.yy_s.data_ptr(), self.body.data_ptr()
+        d.target, d.smooth, d.emit_samples = self.target, self.smooth, 1 if self.emit_samples else 0
+        d.B, d.nF_max, d.n_slots = self.B, self.nF_max, self.N_SLOTS
+        self.frames_host = [torch.zeros(self.B, dtype=torch.int32).pin_memory() for _ in range(self.N_SLOTS)]
+        self.frames_dev = [torch.zeros(self.B, dtype=torch.int32, device=self.device) for _ in range(4)]
+        for k in range(self.N_SLOTS):
+            d.out_dev[k], d.raw_host[k], d.out_host[k] = self.out_bufs[k].data_ptr(), self.raw_host[k].data_ptr(), self.out_host[k].data_ptr()
+            d.frames_host[k] = self.frames_host[k].data_ptr()
+        for k in range(4):
+            d.frames_dev[k] = self.frames_dev[k].data_ptr()
+        handle = ctypes.c_void_p(None)
+        N.check(self.lib.ape_pipeline_create(ctypes.byref(d), ctypes.byref(handle)), "ape_pipeline_create")
+        self._pipe, self._pipe_desc = handle, d
+
+    def __del__(self):
+        pipe, self._pipe = getattr(self, "_pipe", None), None
+        if pipe is not None:
+            try:
+                self.lib.ape_pipeline_destroy(pipe)
+            except Exception:                        # interpreter shutdown: the library may already be gone
+                pass
+
+    def _native_call(self, rows_host, rows_dev, nF, sf_host, flags):
+        """One ``ape_pipeline_submit``; returns (slot, frame0)."""
+        if self._py_dirty:                           # buffers were last touched by the Python-level path: let it finish first
+            torch.cuda.current_stream().synchronize()
+            self.copy_stream.synchronize()
+            self._py_dirty = False
+        self._pipe_busy = True
+        slot = ctypes.c_int(-1)
+        N.check(self.lib.ape_pipeline_submit(self._pipe, rows_host, rows_dev, nF, self.frame, sf_host, flags,
+                                             N.current_stream_ptr(), ctypes.byref(slot)), "ape_pipeline_submit")
+        if nF not in self._launch_cache:
+            self._launch_cache[nF] = 2 + self._lstm_launches(self._lstm_args(nF, 0, None, None)[0])
+        self.launches += self._launch_cache[nF]
+        frame0 = self.frame
+        self.frame += nF
+        self.calls += 1
+        self.submits += 1
+        return slot.value, frame0
+
+    def _leave_native(self):
+        """Before a Python-path call on an estimator that owns a native pipeline: drain the pipeline's streams."""
+        if self._pipe is not None:
+            if self._pipe_busy:
+                N.check(self.lib.ape_pipeline_sync(self._pipe), "ape_pipeline_sync")
+                self._pipe_busy = False
+            self._py_dirty = True
 
     def _lstm_fn(self, variant=None):
         return self.lib.ape_mc_lstm_tc if (variant or self.lstm_variant) == "tc" else self.lib.ape_mc_lstm_fma
@@ -335,6 +411,14 @@ class BatchedEstimator:
         if raw.dtype != torch.float32:
             raise UserWarning("raw rows must be float32 (the wire format, messaging.py)")
         lib, B = self.lib, self.B
+        if (self._pipe is not None and masks is None and layer_ms is None and trace is None and timeline is None and not _plain
+                and _h2d_from is None and stream_frames is None):
+            flags = N.PIPE_CALLER_WAITS | (0 if raw_ready else N.PIPE_INPUT_PENDING)
+            slot, frame0 = self._native_call(None, C_void(raw.data_ptr()), nF, None, flags)
+            self._use_out(slot)
+            return EstimateBatch(self._view(self.msg, nF), self._view(self.std, nF), self._view(self.samples, nF),
+                                 self._view(self.status, nF), frame0)
+        self._leave_native()
         main = torch.cuda.current_stream()
         frame0, sf = (self.frame, None) if stream_frames is None else (0, stream_frames)
         if sf is not None and (sf.dtype != torch.int32 or sf.numel() != B or not sf.is_cuda):
@@ -358,7 +442,7 @@ class BatchedEstimator:
                                       N.ptr(self.msg), N.ptr(self.samples), N.ptr(self.std), None, N.ptr(self.status), stream_ptr),
                     "ape_fk_reduce")
 
-        if self.pipeline and layer_ms is None and trace is None and not _plain:
+        if self.pipeline and self._pipe is None and layer_ms is None and trace is None and not _plain:
             # buffer set of this call: lane (stream + workspace) = call & 1; with lanes each workspace's two copies of layer 0's
             # output alternate as well, so stage 1 + layer 0 may run up to three calls ahead of the big kernels (whichever
             # launch's tail has room for their few dozen CTAs) and never gate the next call's first big layer
@@ -443,6 +527,14 @@ class BatchedEstimator:
         nF = rows.shape[1]
         if rows.shape[0] != self.B or nF > self.nF_max or rows.shape[2] != self.ncols:
             raise UserWarning(f"rows must be [B={self.B}, nF<={self.nF_max}, {self.ncols}], got {rows.shape}")
+        if self._pipe is not None and masks is None:
+            rows = np.ascontiguousarray(rows)
+            sf = None if stream_frames is None else np.ascontiguousarray(np.asarray(stream_frames, dtype=np.int32).reshape(self.B))
+            with torch.cuda.device(self.device):
+                slot, frame0 = self._native_call(C_void(rows.ctypes.data), None, nF, None if sf is None else C_void(sf.ctypes.data),
+                                                 N.PIPE_D2H)
+            return PendingEstimate(self, slot, nF, frame0, None)
+        self._leave_native()
         slot = self.submits % self.N_SLOTS
         self.submits += 1
         if self.slot_event[slot] is not None:
@@ -496,6 +588,7 @@ class BatchedEstimator:
         if rows.shape[0] != self.B or nF > self.nF_max or rows.shape[2] != self.ncols:
             raise UserWarning(f"rows must be [B={self.B}, nF<={self.nF_max}, {self.ncols}], got {rows.shape}")
         with torch.cuda.device(self.device):
+            self._leave_native()
             for ev in self.slot_event:                       # nothing submitted earlier may still be using the staging slots
                 if ev is not None:
                     ev.synchronize()

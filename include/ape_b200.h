@@ -222,6 +222,64 @@ int ape_fk_reduce(const float* preds, int pred_ring, const float* yy_m, const fl
 int ape_msg_from_est(const float* est, int W, const float* body9, int target, int E, int S, float* msg,
                      float* stdev, void* stream);
 
+/* ---- the cross-call pipeline as one host call per batch (ABI 6) --------------------------------------------- */
+/*
+ * What the reference's loop body (estimator.py:174-176) becomes for B streams x nF frames when calls are queued back to back:
+ * stage 1 + MC-LSTM layer 0 on a high-priority side stream (up to three calls ahead), the layers >= 1 + stage 3 on two alternating
+ * lane streams (two calls in flight), the device-to-host copy of the results on a copy stream.  ape_pipeline_submit enqueues all
+ * of it in ONE call (a few dozen CUDA API calls, no Python in between) and returns without waiting; ape_pipeline_wait blocks
+ * until the results of a slot are in pinned host memory.  The tensor-core MC-LSTM only (ape_mc_lstm_tc), mask modes
+ * APE_MASK_PHILOX / APE_MASK_NONE.  The object owns CUDA streams and events and nothing else: every buffer below is the
+ * caller's and must outlive the pipeline.  One host thread per pipeline.
+ *   result buffer layout (device and host, E_max = B * nF_max, S = smooth * n_samples):
+ *     [msg E_max x 25 | std E_max x 6 | status E_max (int32) | samples E_max x S x 6 (if emit_samples)]
+ *   a call of nF < nF_max frames packs its E = B * nF estimates at the front of each part.
+ */
+#define APE_PIPELINE_MAX_SLOTS 8
+#define APE_PIPE_INPUT_PENDING 1  /* rows_dev is still being written on caller_stream: order stage 1 after it */
+#define APE_PIPE_CALLER_WAITS 2   /* caller_stream waits for the call's results (device consumers of out_dev[slot]) */
+#define APE_PIPE_D2H 4            /* copy the results to out_host[slot]; ape_pipeline_wait(slot) then blocks until they landed */
+typedef struct ape_pipeline ape_pipeline;
+typedef struct ape_pipeline_desc {
+    /* stage 1 (ape_features) */
+    int layout, kind, normalize, ncols;
+    const double* xx_m;
+    const double* xx_s;
+    float* raw;                 /* device [B][nF_max][ncols]: where staged host rows are copied to */
+    float* feats;               /* device [B][feat_ring][I] */
+    int feat_ring;
+    /* stage 2 (ape_mc_lstm_tc): model, dims, mask mode, seed, stream_id0, preds, pred_ring, weights_tc, ws_E, tc_flags, B, n_samples
+       as for a direct call; nF, frame0, stream_frames, workspace, layer range and ws_parity are set per call by the pipeline */
+    ape_lstm_args lstm;
+    void* lane_workspace[2];    /* one ape_mc_lstm_tc workspace per lane */
+    /* stage 3 (ape_fk_reduce) */
+    const float* yy_m;
+    const float* yy_s;
+    const float* body9;
+    int target, smooth, emit_samples;
+    /* buffers */
+    int B, nF_max, n_slots;     /* 2 <= n_slots <= APE_PIPELINE_MAX_SLOTS: calls in flight between submit and wait */
+    float* out_dev[APE_PIPELINE_MAX_SLOTS];      /* device result buffers */
+    float* raw_host[APE_PIPELINE_MAX_SLOTS];     /* pinned [B][nF_max][ncols] */
+    float* out_host[APE_PIPELINE_MAX_SLOTS];     /* pinned result buffers */
+    int32_t* frames_dev[4];                      /* optional (all null: not used): per-stream frame counters, device [B] x 4 */
+    int32_t* frames_host[APE_PIPELINE_MAX_SLOTS];/* ... and their pinned staging [B] per slot */
+} ape_pipeline_desc;
+int ape_pipeline_create(const ape_pipeline_desc* desc, ape_pipeline** out);
+int ape_pipeline_destroy(ape_pipeline* p);
+/*
+ * One call of B x nF estimates starting at absolute frame frame0 (or at stream_frames_host[b] per stream, host int32 [B], negative:
+ * the stream sits this call out).  Exactly one of rows_host (any host memory, copied into the slot's pinned staging here) and
+ * rows_dev (device rows, read in place) is non-null.  *slot = the result slot used (out_dev / out_host index); a slot is
+ * reused after n_slots calls, after its previous results have landed.
+ */
+int ape_pipeline_submit(ape_pipeline* p, const float* rows_host, const float* rows_dev, int nF, int frame0,
+                        const int32_t* stream_frames_host, int flags, void* caller_stream, int* slot);
+int ape_pipeline_wait(ape_pipeline* p, int slot);              /* host-blocking: results of `slot` are in out_host[slot] */
+int ape_pipeline_query(ape_pipeline* p, int slot, int* landed);/* non-blocking form */
+int ape_pipeline_sync(ape_pipeline* p);                        /* host-blocking drain of all four streams */
+int ape_pipeline_fence(ape_pipeline* p, void* stream);         /* later submits wait for what `stream` holds now */
+
 /* ---- host self-check hooks (tests only; one row per call, never used by the product path) ------ */
 /* The __host__ __device__ row math of the kernels, compiled for the host so a CPU-only box can pin it. */
 int ape_selfcheck_philox(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4);
@@ -237,6 +295,10 @@ int ape_selfcheck_tcs_schedule(int kgx, int first_step, uint32_t* entries, int m
  * canonical K-major no-swizzle layout of csrc/ape_umma.cuh (a_packed: [cta][K/8][128][8], b_packed: [cta][K/8][N/cta][8]).
  * cta_group 1 | 2; + 16 routes the A operand through tensor memory (tcgen05.st, then the [a_tmem] form of tcgen05.mma). */
 int ape_selftest_umma(const void* a_packed, const void* b_packed, float* d, int N, int K, int cta_group, void* stream);
+/* Measured fp32 FMA peak (TFLOP/s) of the current device: best of `reps` launches of an unrolled register-only FFMA microkernel
+ * (2 x sm_count CTAs x 1024 threads x iters x 128 FFMA).  scratch: >= 2 * sm_count floats on the device.  Synchronises `stream`.
+ * bench.py's roofline denominator for the fp32 LSTM kernel (MEASURED_PEAKS.json has HBM and bf16 tensor figures only). */
+int ape_selftest_ffma_peak(float* scratch, int iters, int reps, float* tflops, void* stream);
 
 #ifdef __cplusplus
 }

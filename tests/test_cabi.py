@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = N.load()
     for name in declared_symbols():
         assert getattr(lib, name) is not None, name
-    assert lib.ape_abi_version() == 5
+    assert lib.ape_abi_version() == 6
 
 
 def test_struct_layout_matches_header():
