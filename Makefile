@@ -1,6 +1,7 @@
 # Builds the C-ABI CUDA library (sm_100a only) and the C oracle.  `python -c "import __graft_entry__ as g; g.build()"` runs this.
 NVCC ?= nvcc
 CSRC := arm_pose_estimation_b200/csrc
+FKFLAGS ?=
 LIB  := arm_pose_estimation_b200/lib/libape_b200.so
 SRCS := $(wildcard $(CSRC)/*.cu)
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/ape_b200.h

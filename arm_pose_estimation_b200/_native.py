@@ -61,6 +61,7 @@ class LstmArgs(C.Structure):
         ("tc_flags", C.c_int),
         ("h0", C.c_void_p),
         ("c0", C.c_void_p),
+        ("reserve_sms", C.c_int),
     ]
 
 

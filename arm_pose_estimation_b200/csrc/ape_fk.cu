@@ -9,8 +9,11 @@
 
 namespace ape {
 
+// Resident CTAs per SM -> registers per thread.  With the next row prefetched the kernel wants 80 registers (O = 12) / 96 (O = 14, 20):
+// at 64 it spills 45 values per pass.  Measured on B200, 32 768 estimates x 100 rows: O = 12: 8 / 6 / 5 CTAs = 0.080 / 0.068 / 0.070 ms,
+// O = 14: 0.109 / 0.089 / 0.076 ms.
 #ifndef APE_FK_MIN_BLOCKS
-#define APE_FK_MIN_BLOCKS 8      // 64 registers: 32 resident warps per SM instead of 16 (B200, 32 768 estimates x 100 rows: 0.127 -> 0.100 ms)
+#define APE_FK_MIN_BLOCKS(TARGET) ((TARGET) == APE_TARGET_ORI_CAL_LARM_UARM ? 6 : 5)
 #endif
 #ifndef APE_FK_WARPS
 #define APE_FK_WARPS 4
@@ -59,7 +62,7 @@ __device__ __forceinline__ Quat<float> warp_sum_normalised(Quat<float> s, unsign
 }
 
 template <int TARGET, bool FROM_EST>
-__global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_reduce_kernel(FkArgs a) {
+__global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGET)) fk_reduce_kernel(FkArgs a) {
     constexpr int O = TARGET == APE_TARGET_ORI_CAL_LARM_UARM ? 12 : (TARGET == APE_TARGET_ORI_CAL_LARM_UARM_HIPS ? 14 : 20);
     constexpr int W = TARGET == APE_TARGET_ORI_CAL_LARM_UARM ? 14 : 21;
     __shared__ float s_msg[FK_WARPS_PER_CTA * 2][32];
@@ -96,6 +99,34 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
     bool bad = false;
 
     int rw = lane / a.n, rs = lane - rw * a.n;        // this lane's row i = rw * n + rs (window frame, MC sample), advanced by 16 per pass
+    // first prediction row of window frame rw (frames clamp to frame 0, estimator.py:114-115; the ring slot costs an integer
+    // division, so it is re-derived only when the lane moves on to the next window frame - not per row)
+    auto frame_rows = [&](int w) {
+        int fw = f - a.smooth + 1 + w;
+        fw = fw < 0 ? 0 : fw;
+        return a.preds + ((size_t)b * a.pred_ring + (size_t)(fw % a.pred_ring)) * a.n * O;
+    };
+    const float* wrows = FROM_EST ? nullptr : frame_rows(rw);
+    // The prediction row of the NEXT pass is requested before this pass's arithmetic (a lane reads 48 - 80 bytes per pass: with the
+    // load issued where it is consumed, a third of the kernel's warp-cycles were spent waiting for it)
+    float pre[O];
+    auto request = [&](const float* row) {
+        if (O % 4 == 0) {                                        // 48 / 80-byte rows: 16-byte loads
+#pragma unroll
+            for (int j = 0; j < O / 4; ++j) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(row) + j);
+                pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w;
+            }
+        } else {                                                 // 56-byte rows: 8-byte loads
+#pragma unroll
+            for (int j = 0; j < O / 2; ++j) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(row) + j);
+                pre[2 * j] = v.x; pre[2 * j + 1] = v.y;
+            }
+        }
+    };
+    if (!FROM_EST && lane < S) request(wrows + rs * O);
+    float2* smp = a.samples ? reinterpret_cast<float2*>(a.samples + ((size_t)e * S + lane) * 6) : nullptr;   // this lane's row of the pass
     for (int i0 = 0; i0 < S; i0 += FK_LANES) {
         const int i = i0 + lane;
         const bool live = i < S;
@@ -113,24 +144,16 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
             r.uarm = {src[k + 4], src[k + 5], src[k + 6], src[k + 7]};
             if (W == 21) r.hips = {src[k + 8], src[k + 9], src[k + 10], src[k + 11]};
         } else if (live) {
-            const int w = rw, s = rs;
-            int fw = f - a.smooth + 1 + w;                       // window frames clamp to frame 0 (estimator.py:114-115)
-            fw = fw < 0 ? 0 : fw;
-            const float* row = a.preds + (((size_t)b * a.pred_ring + (fw % a.pred_ring)) * a.n + s) * O;
             float p[O];
-            if (O % 4 == 0) {                                    // 48 / 80-byte rows: 16-byte loads
 #pragma unroll
-                for (int j = 0; j < O / 4; ++j) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + j);
-                    p[4 * j] = v.x; p[4 * j + 1] = v.y; p[4 * j + 2] = v.z; p[4 * j + 3] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < O / 2; ++j) {
-                    const float2 v = __ldg(reinterpret_cast<const float2*>(row) + j);
-                    p[2 * j] = v.x; p[2 * j + 1] = v.y;
-                }
+            for (int j = 0; j < O; ++j) p[j] = pre[j];
+            // advance to the next pass's row (no integer division per row) and request it
+            rs += FK_LANES;
+            if (rs >= a.n) {
+                do { rs -= a.n; ++rw; } while (rs >= a.n);
+                if (rw < a.smooth) wrows = frame_rows(rw);
             }
+            if (i + FK_LANES < S) request(wrows + rs * O);
 #pragma unroll
             for (int j = 0; j < O; ++j) p[j] = fmaf(p[j], s_s[j], s_m[j]);     // estimator.py:108-109
             bool rb = false;
@@ -162,11 +185,11 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
                 for (int j = 0; j < 6; ++j) psum[j] += pv[j];
                 psum[6] += r.shoulder.x; psum[7] += r.shoulder.y; psum[8] += r.shoulder.z;
             }
-            if (a.samples) {
-                float2* dst = reinterpret_cast<float2*>(a.samples + ((size_t)e * S + i) * 6);
-                dst[0] = make_float2(pv[0], pv[1]);
-                dst[1] = make_float2(pv[2], pv[3]);
-                dst[2] = make_float2(pv[4], pv[5]);
+            if (smp) {
+                smp[0] = make_float2(pv[0], pv[1]);
+                smp[1] = make_float2(pv[2], pv[3]);
+                smp[2] = make_float2(pv[4], pv[5]);
+                smp += FK_LANES * 3;
             }
             if (a.est_rows) {
                 float* dst = a.est_rows + ((size_t)e * S + i) * W;
@@ -179,8 +202,6 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
                 if (W == 21) { dst[k++] = r.hips.w; dst[k++] = r.hips.x; dst[k++] = r.hips.y; dst[k++] = r.hips.z; }
             }
         }
-        rs += FK_LANES;                                              // (no integer division per row)
-        while (rs >= a.n) { rs -= a.n; ++rw; }
     }
 
     // ---- reduction over the S rows --------------------------------------------------------------------
@@ -210,7 +231,7 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS) fk_r
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         const float m1 = warp_sum(d1[j], hm) * invS, m2 = warp_sum(d2[j], hm) * invS;
-        sd[j] = sqrtf(fmaxf(m2 - m1 * m1, 0.0f));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd[j]) : "f"(fmaxf(m2 - m1 * m1, 0.0f)));
     }
     const unsigned any_bad = __ballot_sync(hm, bad) & hm;
 

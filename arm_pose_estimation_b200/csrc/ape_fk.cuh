@@ -10,7 +10,11 @@ namespace ape {
 APE_HD double inv_sqrt(double x) { return 1.0 / sqrt(x); }
 APE_HD float inv_sqrt(float x) {
 #ifdef __CUDA_ARCH__
-    return rsqrtf(x);
+    // the bare MUFU.RSQ (rsqrtf() wraps it in a denormal fix-up: 5 more instructions, six times per row); arguments here are
+    // squared norms of O(1) vectors - a denormal one is reported as a degenerate row (six_to_quat: `bad`)
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 #else
     return 1.0f / sqrtf(x);
 #endif
@@ -31,26 +35,26 @@ template <typename F> APE_HD Quat<F> six_to_quat(const F* c, bool& bad) {
     const F b2x = ux * i2, b2y = uy * i2, b2z = uz * i2;
     const F b3x = b1y * b2z - b1z * b2y, b3y = b1z * b2x - b1x * b2z, b3z = b1x * b2y - b1y * b2x;
     // a zero / non-finite / absurdly long column (squared norms: the bound is 1e30 squared, infinity in float)
-    if (!(s1 > F(0)) || !(s2 > F(0)) || !(s1 < F(1e30) * F(1e30)) || !(s2 < F(1e30) * F(1e30))) bad = true;
+    const F smin = s1 < s2 ? s1 : s2, smax = s1 < s2 ? s2 : s1;
+    // (a NaN norm fails the first test whichever side it took; float: a norm below 1e-18 counts as zero - its square is denormal)
+    if (!(smin > (sizeof(F) == 4 ? F(1e-36) : F(0))) || !(smax < F(1e30) * F(1e30))) bad = true;
     // R = [b1 b2 b3] as columns: r_ij = row i, column j
     const F r00 = b1x, r01 = b2x, r02 = b3x, r10 = b1y, r11 = b2y, r12 = b3y, r20 = b1z, r21 = b2z, r22 = b3z;
     const F fw = F(1) + r00 + r11 + r22, fx = F(1) + r00 - r11 - r22;
     const F fy = F(1) - r00 + r11 - r22, fz = F(1) - r00 - r11 + r22;
-    Quat<F> q;
-    if (fw >= fx && fw >= fy && fw >= fz) {
-        const F s = F(0.5) * inv_sqrt(fw);
-        q = {fw * s, (r21 - r12) * s, (r02 - r20) * s, (r10 - r01) * s};
-    } else if (fx >= fy && fx >= fz) {
-        const F s = F(0.5) * inv_sqrt(fx);
-        q = {(r21 - r12) * s, fx * s, (r01 + r10) * s, (r02 + r20) * s};
-    } else if (fy >= fz) {
-        const F s = F(0.5) * inv_sqrt(fy);
-        q = {(r02 - r20) * s, (r01 + r10) * s, fy * s, (r12 + r21) * s};
-    } else {
-        const F s = F(0.5) * inv_sqrt(fz);
-        q = {(r10 - r01) * s, (r02 + r20) * s, (r12 + r21) * s, fz * s};
-    }
-    const F inv = inv_sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);   // eigh returns a unit vector
+    // The four conversion branches are the four rows of the symmetric matrix 4 q q^T (row w = (4w^2, 4wx, 4wy, 4wz), ...): each is
+    // a multiple of q, and the row of the largest diagonal entry is the well-conditioned one.  Selecting that row component by
+    // component and normalising ONCE is branch-free - on the GPU the four-way branch diverged inside every warp and carried its own
+    // reciprocal square root - and is the same quaternion (eigh returns a unit vector, made w >= 0 by :543-544).
+    const F wx = r21 - r12, wy = r02 - r20, wz = r10 - r01, xy = r01 + r10, xz = r02 + r20, yz = r12 + r21;
+    const bool wx_w = fw >= fx, yz_y = fy >= fz;                 // winners of the two pairs, then of the final
+    const F m01 = wx_w ? fw : fx, m23 = yz_y ? fy : fz;
+    const bool first = m01 >= m23;
+    // candidate rows: W = (fw, wx, wy, wz), X = (wx, fx, xy, xz), Y = (wy, xy, fy, yz), Z = (wz, xz, yz, fz)
+    const F aw = wx_w ? fw : wx, ax = wx_w ? wx : fx, ay = wx_w ? wy : xy, az = wx_w ? wz : xz;
+    const F bw = yz_y ? wy : wz, bx = yz_y ? xy : xz, by = yz_y ? fy : yz, bz = yz_y ? yz : fz;
+    Quat<F> q = {first ? aw : bw, first ? ax : bx, first ? ay : by, first ? az : bz};
+    const F inv = inv_sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
     const F sg = q.w < F(0) ? -inv : inv;
     return {q.w * sg, q.x * sg, q.y * sg, q.z * sg};
 }

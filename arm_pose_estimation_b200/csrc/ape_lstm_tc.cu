@@ -726,6 +726,10 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
     // CTA pair at least one tile (below that a lone tile is faster through two one-layer launches: its two layers cannot overlap
     // on the epilogue warps of one pair); tc_flags forces either way.
     const bool pair_ok = tc_pairs_layers(g, tiles1, sm_count);
+    // SMs the launches of layers >= 1 leave free (a whole number of SM pairs): a concurrent stage 1 + layer 0 of the NEXT call - a few
+    // CTAs on a high-priority stream - then never has to wait for a persistent launch to retire CTAs
+    if (g->reserve_sms < 0 || g->reserve_sms > sm_count - 2) return APE_ERR_BAD_ARG;
+    const int sm_big = sm_count - ((g->reserve_sms + 1) & ~1);
     for (int l = 0; l < l_end;) {
         const uint8_t* wl_l = wl;
         wl += tc_layer_bytes(l, g->I, H);
@@ -734,13 +738,14 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
         if (pair_ok && l >= 1 && l + 1 < l_end) {
             const tc::TcLayerArgs b = layer_args(l + 1, wl);
             wl += tc_layer_bytes(l + 1, g->I, H);
-            rc = tcw::launch_pair(a, b, sm_count, st);
+            rc = tcw::launch_pair(a, b, sm_big, st);
             if (rc != APE_OK) return rc;
             if (prof) { APE_CUDA_TRY(cudaEventRecord(ev[l + 1], st)); APE_CUDA_TRY(cudaEventRecord(ev[l + 2], st)); }   // layer_ms[l] = the pair, [l+1] = 0
             l += 2;
             continue;
         }
-        rc = H == 128 ? tc::launch<128>(a, sm_count, st) : H == 64 ? tc::launch<64>(a, sm_count, st) : tcs::launch_layer(H, a, sm_count, st);
+        const int sms = l == 0 ? sm_count : sm_big;
+        rc = H == 128 ? tc::launch<128>(a, sms, st) : H == 64 ? tc::launch<64>(a, sms, st) : tcs::launch_layer(H, a, sms, st);
         if (rc != APE_OK) return rc;
         if (prof) APE_CUDA_TRY(cudaEventRecord(ev[l + 1], st));
         ++l;

@@ -137,6 +137,7 @@ class BatchedEstimator:
         # tensor-core path, H = 128, L >= 3: 0 = pairs of layers >= 1 as one wavefront launch when the batch fills the GPU,
         # 1 = always one launch per layer, 2 = always wavefront pairs (include/ape_b200.h: ape_lstm_args.tc_flags)
         self.tc_flags = int(os.environ.get("APE_TC_FLAGS", "0")) if tc_flags is None else int(tc_flags)     # (the variable: A/B runs of bench.py)
+        self.reserve_sms = 0
         self.ncols = LAYOUT_NCOLS[self.layout]
         dev, f32 = self.device, torch.float32
         with torch.cuda.device(dev):
@@ -206,6 +207,12 @@ class BatchedEstimator:
             #    fills only part of the GPU (400 tiles over 74 pairs = 5.4 rounds), and the pairs that finish early pick up the
             #    next call's layer instead of idling until the launch drains.  At most two calls are in flight.
             self.pipeline = bool(pipeline) and self.lstm_variant == "tc"
+            # With the pipeline the persistent launches of the layers >= 1 leave ONE SM pair free for the side stream: stage 1 + layer 0
+            # of the next calls (<= 8 CTAs) otherwise only get SMs in the ~50 us in which a big launch retires its CTAs, and a call
+            # whose layer 0 misses that window stalls its lane.  Measured (uarm 1024 x 100, B200): 0 -> 2 reserved SMs: device-resident
+            # 3.445M -> 3.498M est/s, end to end (H2D of the rows in front of stage 1) 3.206M -> 3.483M; 4 reserved SMs: the same.
+            if self.pipeline:
+                self.reserve_sms = int(os.environ.get("APE_RESERVE_SMS", "2"))
             # (high priority: its few dozen CTAs take the first SMs any big launch frees, so layer 0 is ready well before its call's turn)
             self.side_stream = torch.cuda.Stream(device=dev, priority=-1) if self.pipeline else None
             self.lanes = bool(lanes) and self.pipeline
@@ -367,6 +374,7 @@ class BatchedEstimator:
         a.weights_tc = None if self.tc_weights is None else self.tc_weights.data_ptr()
         # the workspace is laid out for the largest call, so short calls in flight beside full ones agree on every offset
         a.ws_E, a.tc_flags = B * self.nF_max, self.tc_flags
+        a.reserve_sms = self.reserve_sms
         return a, md
 
     # ---- the reference's three per-frame calls, one by one (estimator.py:174-176) ------------------------------------

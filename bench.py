@@ -51,6 +51,7 @@ WORKLOAD_TEXT = {
     "pocket_1024x100": "watch+phone pocket LSTM estimator (the model of BASELINE configs[1]), 1024 concurrent streams x 100 MC samples",
 }
 METRIC, UNIT = "mc_sampled_arm_pose_estimates_per_sec", "estimates/s"
+DEBUG_STEPS = os.environ.get("APE_BENCH_DEBUG", "0") == "1"
 
 
 def tc_kernel_name(H, pair=False):
@@ -373,11 +374,18 @@ def run_ours(args, rank, world, local_rank):
             be.step_device(frames_dev[f], raw_ready=True)
         barrier()
         launches0 = be.launches
+        step_ev = []
         ev0.record()
         for f in range(W, W + K):
             be.step_device(frames_dev[f], raw_ready=True)     # inputs resident in HBM before the timed region
+            if DEBUG_STEPS:
+                step_ev.append(torch.cuda.Event(enable_timing=True))
+                step_ev[-1].record()
         ev1.record()
         barrier()
+    if DEBUG_STEPS:                                           # APE_BENCH_DEBUG=1: completion time of every step of the timed region, per rank
+        print(f"rank {rank}: total {ev0.elapsed_time(ev1):.3f} ms; step completions (ms): "
+              + " ".join(f"{ev0.elapsed_time(e):.3f}" for e in step_ev), file=sys.stderr, flush=True)
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = be.launches - launches0
     clocks = clk.summary()

@@ -147,6 +147,11 @@ typedef struct ape_lstm_args {
        or neither; needs n_samples == 1 (a caller with per-sample states passes the samples as estimates) */
     const float* h0;
     const float* c0;
+    /* ---- ABI 6 ---- */
+    /* tensor-core path: SMs (rounded up to whole SM pairs) that the persistent launches of the layers >= 1 leave free, so that the
+       few CTAs of stage 1 + layer 0 of the NEXT call (a high-priority side stream, ape_pipeline_submit) start at once instead of
+       waiting for a persistent launch to retire CTAs; 0 = use every SM */
+    int reserve_sms;
 } ape_lstm_args;
 
 int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
