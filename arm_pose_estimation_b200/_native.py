@@ -24,7 +24,7 @@ KSLICE = 16                      # csrc/ape_lstm_pack.h: APE_KSLICE
 SYMBOLS = (
     "ape_abi_version", "ape_last_cuda_error", "ape_device_info", "ape_lstm_blob_floats", "ape_features", "ape_features_push",
     "ape_mc_lstm_workspace_bytes", "ape_mc_lstm_fma", "ape_mc_lstm_tc_supported", "ape_lstm_tc_blob_bytes",
-    "ape_mc_lstm_tc_workspace_bytes", "ape_mc_lstm_tc_workspace_bytes_all_steps", "ape_mc_lstm_tc", "ape_mc_lstm_tc_launch_count", "ape_philox_masks", "ape_ff_blob_floats", "ape_mc_ff", "ape_dense_act", "ape_fk_reduce", "ape_msg_from_est",
+    "ape_mc_lstm_tc_workspace_bytes", "ape_mc_lstm_tc_workspace_bytes_all_steps", "ape_mc_lstm_tc", "ape_mc_lstm_tc_launch_count", "ape_mc_lstm_tcx_supported", "ape_lstm_tcx_blob_bytes", "ape_mc_lstm_tcx_workspace_bytes", "ape_philox_masks", "ape_ff_blob_floats", "ape_mc_ff", "ape_dense_act", "ape_fk_reduce", "ape_msg_from_est",
     "ape_pipeline_create", "ape_pipeline_destroy", "ape_pipeline_submit", "ape_pipeline_wait", "ape_pipeline_query", "ape_pipeline_sync",
     "ape_pipeline_fence",
     "ape_selfcheck_philox", "ape_selfcheck_keep8", "ape_selfcheck_features", "ape_selfcheck_row_pose", "ape_selfcheck_tcs_schedule",
@@ -62,6 +62,7 @@ class LstmArgs(C.Structure):
         ("h0", C.c_void_p),
         ("c0", C.c_void_p),
         ("reserve_sms", C.c_int),
+        ("weights_tcx", C.c_void_p),
     ]
 
 
@@ -139,6 +140,12 @@ def load():
     lib.ape_mc_lstm_tc.argtypes = [C.POINTER(LstmArgs), vp]
     lib.ape_mc_lstm_tc_launch_count.restype = i32
     lib.ape_mc_lstm_tc_launch_count.argtypes = [C.POINTER(LstmArgs), C.POINTER(i32)]
+    lib.ape_mc_lstm_tcx_supported.restype = i32
+    lib.ape_mc_lstm_tcx_supported.argtypes = [i32, i32, i32, i32]
+    lib.ape_lstm_tcx_blob_bytes.restype = i32
+    lib.ape_lstm_tcx_blob_bytes.argtypes = [i32, i32, i32, C.POINTER(C.c_int64)]
+    lib.ape_mc_lstm_tcx_workspace_bytes.restype = i32
+    lib.ape_mc_lstm_tcx_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(u64)]
     lib.ape_philox_masks.restype = i32
     lib.ape_philox_masks.argtypes = [u64, u32, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp]
     lib.ape_ff_blob_floats.restype = i32
@@ -229,6 +236,22 @@ def workspace_bytes(I, H, L, T, O, E, n, tensor_core=False, all_steps=False):
 
 def tc_supported(I, H, L, O):
     return bool(load().ape_mc_lstm_tc_supported(I, H, L, O))
+
+
+def tcx_supported(I, H, L, O):
+    return bool(load().ape_mc_lstm_tcx_supported(I, H, L, O))
+
+
+def tcx_blob_bytes(I, H, L):
+    out = C.c_int64(0)
+    check(load().ape_lstm_tcx_blob_bytes(I, H, L, C.byref(out)), "ape_lstm_tcx_blob_bytes")
+    return out.value
+
+
+def tcx_workspace_bytes(I, H, L, T, O, E, n):
+    out = C.c_uint64(0)
+    check(load().ape_mc_lstm_tcx_workspace_bytes(I, H, L, T, O, E, n, C.byref(out)), "ape_mc_lstm_tcx_workspace_bytes")
+    return out.value
 
 
 def tc_blob_bytes(I, H, L):

@@ -618,7 +618,7 @@ extern "C" int ape_mc_lstm_tc_launch_count(const ape_lstm_args* g, int* launches
     const long long rows = (long long)g->B * g->nF * g->n_samples;
     const int l_begin = (g->layer_begin == 0 && g->layer_end == 0) ? 0 : g->layer_begin;
     const int l_end = (g->layer_begin == 0 && g->layer_end == 0) ? g->L : g->layer_end;
-    const bool pair_ok = tc_pairs_layers(g, (rows + 255) / 256, sm_count);
+    const bool pair_ok = g->tc_flags != 3 && tc_pairs_layers(g, (rows + 255) / 256, sm_count);
     int n = 0;
     for (int l = l_begin; l < l_end;) { ++n; l += (pair_ok && l >= 1 && l + 1 < l_end) ? 2 : 1; }
     *launches = n + (g->all_steps ? 1 : 0);
@@ -629,6 +629,7 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
     using namespace ape;
     int rc = check_lstm_args(g);
     if (rc != APE_OK) return rc;
+    if (g->tc_flags == 3) return ape::tcx::run(g, (cudaStream_t)stream);      // split-precision variant (csrc/ape_lstm_tcx.cu)
     if (!ape_mc_lstm_tc_supported(g->I, g->H, g->L, g->O)) return APE_ERR_UNSUPPORTED;
     if (g->all_steps && (g->layer_begin != 0 || g->layer_end != 0)) return APE_ERR_UNSUPPORTED;
     if (g->h0 || g->c0) return APE_ERR_UNSUPPORTED;            // a caller-supplied initial state runs on the fp32 path

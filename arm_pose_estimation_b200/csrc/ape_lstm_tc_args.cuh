@@ -24,6 +24,7 @@ struct TcLayerArgs {
     int in_rpc_shift;          // IN_SHARED_UNITS: log2(rpc) of the producing layer
     int in_mode;
     const void* in;
+    const void* in_lo;         // split-precision kernel (ape_lstm_tcx.cu): the lo halves of the input units (in = the hi halves)
     int feat_ring, nF, frame0, rows, n;
     const int32_t* stream_frames;   // per-stream frame counters (null: frame0 for all); < 0: the stream sits this call out
     int mask_mode;
@@ -34,6 +35,7 @@ struct TcLayerArgs {
     uint32_t stream_id0;
     uint32_t keep_thr16;
     uint4* out_units;          // [pair tile][T][cta][k-group][128 rows] 16-byte units of fp16 (h_t * out_scale), or null
+    uint4* out_units_lo;       // split-precision kernel: the lo halves (fp16(v - fp16(v))) of the same units
     float out_scale;           // the consumer's 1/(1-p): scaling BEFORE the fp16 rounding keeps it a single rounding
     const float* Wo;
     const float* bo;
@@ -121,4 +123,15 @@ size_t layer_bytes(int H);                      // bytes of one layer's pieces (
 size_t scratch_bytes(int H, int sm_count);      // per-CTA cell-state scratch of one launch
 int launch_pair(const tc::TcLayerArgs& a, const tc::TcLayerArgs& b, int sm_count, cudaStream_t st);
 }  // namespace tcw
+
+namespace tcx {
+// split-precision kernel (ape_lstm_tcx.cu): every operand an fp16 pair hi + lo, three tensor-core passes per product, ex2 / rcp cell
+bool supported(int H, int I, int O);
+size_t layer_bytes(int layer, int I);            // bytes of one layer's pieces (TcLayerArgs::Ww), both CTAs
+size_t scratch_bytes(int sm_count);              // per-CTA cell-state scratch of one launch
+int launch_layer(const tc::TcLayerArgs& a, int sm_count, cudaStream_t st);
+int run(const ape_lstm_args* g, cudaStream_t st);    // all layers of a call (ape_mc_lstm_tc with tc_flags == 3)
+size_t blob_bytes(int I, int L);
+size_t workspace_bytes(int L, int T, long long E, int n_samples);
+}  // namespace tcx
 }  // namespace ape

@@ -35,12 +35,15 @@ struct ape_pipeline {
 extern "C" int ape_pipeline_create(const ape_pipeline_desc* d, ape_pipeline** out) {
     if (!d || !out) return APE_ERR_BAD_ARG;
     if (d->n_slots < 2 || d->n_slots > MAX_SLOTS || d->B < 1 || d->nF_max < 1 || d->ncols < 1 || d->smooth < 1) return APE_ERR_BAD_ARG;
-    if (!d->raw || !d->feats || !d->lstm.weights_tc || !d->lstm.preds || !d->lane_workspace[0] || !d->lane_workspace[1] || !d->body9)
+    const bool split = d->lstm.tc_flags == 3;                  // the split-precision variant brings its own blob
+    if (!d->raw || !d->feats || !(split ? d->lstm.weights_tcx : d->lstm.weights_tc) || !d->lstm.preds || !d->lane_workspace[0] ||
+        !d->lane_workspace[1] || !d->body9)
         return APE_ERR_BAD_ARG;
     for (int s = 0; s < d->n_slots; ++s)
         if (!d->out_dev[s] || !d->raw_host[s] || !d->out_host[s]) return APE_ERR_BAD_ARG;
     if (d->lstm.mask_mode == APE_MASK_INJECTED) return APE_ERR_UNSUPPORTED;      // injected masks change per call: the caller's path
-    if (!ape_mc_lstm_tc_supported(d->lstm.I, d->lstm.H, d->lstm.L, d->lstm.O)) return APE_ERR_UNSUPPORTED;
+    if (!(split ? ape_mc_lstm_tcx_supported(d->lstm.I, d->lstm.H, d->lstm.L, d->lstm.O)
+                : ape_mc_lstm_tc_supported(d->lstm.I, d->lstm.H, d->lstm.L, d->lstm.O))) return APE_ERR_UNSUPPORTED;
     ape_pipeline* p = new (std::nothrow) ape_pipeline();
     if (!p) return APE_ERR_BAD_ARG;
     p->d = *d;

@@ -182,14 +182,20 @@ class BatchedEstimator:
             # Tensor cores when the fp16-operand result stays within tc_tolerance_m of the fp32 kernel on a probe batch of
             # THIS model's weights (and the batch has at least tc_min_rows rows: the measured crossover against the fp32
             # kernel is below one row - profiles/r1_crossover.md - so the default does not restrict).
-            self.tc_weights = None
-            self.tc_probe_error_m = None
+            # "tcx" = the split-precision tensor-core kernel (csrc/ape_lstm_tcx.cu, H = 128): fp16 pairs hi + lo, three passes per product,
+            # ex2 / rcp cell update - what "auto" takes when the single-pass probe fails, before it falls back to the fp32 kernel.
+            self.tc_weights = self.tcx_weights = None
+            self.tc_probe_error_m = self.tcx_probe_error_m = None
+            self.tc_split = False
             self.lstm_variant = "fp32"
-            if lstm_variant not in ("auto", "fp32", "tc"):
-                raise UserWarning(f"lstm_variant must be 'auto', 'fp32' or 'tc', got {lstm_variant!r}")
+            if lstm_variant not in ("auto", "fp32", "tc", "tcx"):
+                raise UserWarning(f"lstm_variant must be 'auto', 'fp32', 'tc' or 'tcx', got {lstm_variant!r}")
             tc_ok = N.tc_supported(self.I, self.H, self.L, self.O) and self.T <= 40
+            tcx_ok = N.tcx_supported(self.I, self.H, self.L, self.O) and self.T <= 40
             if lstm_variant == "tc" and not tc_ok:
                 raise UserWarning(f"the tensor-core LSTM kernel does not support H={self.H}, L={self.L}")
+            if lstm_variant == "tcx" and not tcx_ok:
+                raise UserWarning(f"the split-precision tensor-core LSTM kernel does not support H={self.H}, L={self.L}, O={self.O}")
             if lstm_variant == "tc" or (lstm_variant == "auto" and tc_ok and B * nF * self.n >= tc_min_rows):
                 self.tc_weights = torch.from_numpy(nn_models.pack_lstm_weights_tc(state)).to(dev)
                 assert self.tc_weights.numel() == N.tc_blob_bytes(self.I, self.H, self.L)
@@ -199,6 +205,15 @@ class BatchedEstimator:
                 self.tc_probe_error_m = self._probe_tc_error()
                 if lstm_variant == "tc" or self.tc_probe_error_m <= tc_tolerance_m:
                     self.lstm_variant = "tc"
+            if lstm_variant == "tcx" or (lstm_variant == "auto" and self.lstm_variant != "tc" and tcx_ok and B * nF * self.n >= tc_min_rows):
+                self.tcx_weights = torch.from_numpy(nn_models.pack_lstm_weights_tcx(state)).to(dev)
+                assert self.tcx_weights.numel() == N.tcx_blob_bytes(self.I, self.H, self.L)
+                self.tcx_probe_error_m = self._probe_tc_error("tcx")
+                if lstm_variant == "tcx" or self.tcx_probe_error_m <= tc_tolerance_m:
+                    self.lstm_variant, self.tc_split, self.tc_flags = "tc", True, 3
+                    ws_x = N.tcx_workspace_bytes(self.I, self.H, self.L, self.T, self.O, B * nF, self.n) + 1024
+                    if ws_x > self.workspace.numel():
+                        self.workspace = torch.empty(ws_x, dtype=torch.uint8, device=dev)
             # cross-call software pipeline (tensor-core path), two levels:
             #  * stage 1 + LSTM layer 0 of call k+1 (a few dozen CTAs) run on a side stream under call k's big layer kernels;
             #    layer 0's output is double-buffered by call parity;
@@ -292,7 +307,7 @@ class BatchedEstimator:
             self._py_dirty = True
 
     def _lstm_fn(self, variant=None):
-        return self.lib.ape_mc_lstm_tc if (variant or self.lstm_variant) == "tc" else self.lib.ape_mc_lstm_fma
+        return self.lib.ape_mc_lstm_tc if (variant or self.lstm_variant) in ("tc", "tcx") else self.lib.ape_mc_lstm_fma
 
     def _lstm_launches(self, a):
         """Kernels the LSTM stage launches for the argument block ``a`` (pairs of layers of an H = 128 model count once)."""
@@ -303,20 +318,25 @@ class BatchedEstimator:
         N.check(self.lib.ape_mc_lstm_tc_launch_count(a, ctypes.byref(n)), "ape_mc_lstm_tc_launch_count")
         return n.value
 
-    def _probe_tc_error(self, n_est=16, n_samples=64):
-        """Max |position| difference (metres) between the tensor-core and the fp32 LSTM kernels on a probe batch:
-        N(0,1) normalised windows, the same Philox masks for both (the keying does not depend on the kernel)."""
+    def _probe_tc_error(self, which="tc", n_est=16, n_samples=64):
+        """Max |position| difference (metres) between a tensor-core LSTM kernel (``which``: "tc" single pass | "tcx" split precision)
+        and the fp32 kernel on a probe batch: N(0,1) normalised windows, the same Philox masks for both (the keying does not depend
+        on the kernel)."""
         dev = self.device
         g = torch.Generator(device="cpu").manual_seed(1234)
         x = torch.randn((n_est, self.T, self.I), generator=g, dtype=torch.float32).to(dev)
         ws = torch.empty(max(N.workspace_bytes(self.I, self.H, self.L, self.T, self.O, n_est, n_samples),
+                             N.tcx_workspace_bytes(self.I, self.H, self.L, self.T, self.O, n_est, n_samples) if which == "tcx" else
                              N.workspace_bytes(self.I, self.H, self.L, self.T, self.O, n_est, n_samples, tensor_core=True)),
                          dtype=torch.uint8, device=dev)
         outs = []
-        for variant in ("fp32", "tc"):
+        for variant in ("fp32", which):
             preds = torch.zeros((n_est, 1, n_samples, self.O), dtype=torch.float32, device=dev)
             a = N.LstmArgs()
-            a.weights, a.weights_tc = self.weights.data_ptr(), self.tc_weights.data_ptr()
+            a.weights = self.weights.data_ptr()
+            a.weights_tc = None if self.tc_weights is None else self.tc_weights.data_ptr()
+            if variant == "tcx":
+                a.weights_tcx, a.tc_flags = self.tcx_weights.data_ptr(), 3
             a.I, a.H, a.L, a.T, a.O = self.I, self.H, self.L, self.T, self.O
             a.dropout_p = self.p
             a.x_dense, a.feat_ring_buf, a.feat_ring = x.data_ptr(), None, 0
@@ -375,6 +395,7 @@ class BatchedEstimator:
         # the workspace is laid out for the largest call, so short calls in flight beside full ones agree on every offset
         a.ws_E, a.tc_flags = B * self.nF_max, self.tc_flags
         a.reserve_sms = self.reserve_sms
+        a.weights_tcx = None if self.tcx_weights is None else self.tcx_weights.data_ptr()
         return a, md
 
     # ---- the reference's three per-frame calls, one by one (estimator.py:174-176) ------------------------------------

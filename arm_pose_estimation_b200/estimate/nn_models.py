@@ -122,6 +122,56 @@ def pack_lstm_weights_tc(state):
     return np.ascontiguousarray(np.concatenate(parts))
 
 
+def pack_lstm_weights_tcx(state):
+    """Reference state dict -> the blob of the SPLIT-PRECISION tensor-core kernel (``csrc/ape_lstm_tcx.cu``, H = 128), as uint8 bytes.
+
+    Every weight enters as an fp16 pair ``hi = fp16(w)``, ``lo = fp16(w - hi)``; the i, f, o columns are halved first (exact), so the
+    accumulator is the ex2 argument of the cell update up to one constant.  Per layer, CTA ``r`` of the pair and 32-unit chunk ``c``
+    (gate columns as in ``pack_lstm_weights_tc``) four K-major tiles ``[k-group][64][8]``: ``Wx_hi`` with one extra K = 16 step whose
+    rows 0 and 1 hold the scaled bias as an fp16 pair (the kernel multiplies it by a tile of ones), ``Wx_lo``, ``Wh_hi``, ``Wh_lo``.
+    After all layers the output layer as in ``pack_lstm_weights_tc`` (fp16 rounding and remainder, 16 columns)."""
+    st = {k: np.asarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
+          for k, v in state.items()}
+    I, H, L, O = lstm_dims(st)
+    if H != 128:
+        raise UserWarning("the split-precision tensor-core kernel takes H = 128")
+    parts, nl = [], np.arange(64)
+
+    def tiles(w):                                                  # [cols, K] fp32 -> (hi, lo) K-major uint8 tiles
+        hi = w.astype(np.float16)
+        lo = (w - hi.astype(np.float32)).astype(np.float16)
+        cols, k = w.shape
+        return [np.ascontiguousarray(t.reshape(cols, k // 8, 8).transpose(1, 0, 2)).view(np.uint8).ravel() for t in (hi, lo)]
+
+    for l in range(L):
+        w_ih, w_hh = st[f"lstm.weight_ih_l{l}"], st[f"lstm.weight_hh_l{l}"]
+        bias = st[f"lstm.bias_ih_l{l}"] + st[f"lstm.bias_hh_l{l}"]
+        kin_pad = -(-w_ih.shape[1] // N.KSLICE) * N.KSLICE if l == 0 else H
+        for r in range(2):
+            n = 64 * r + nl
+            scale = np.where((n % 4) != 2, np.float32(0.5), np.float32(1.0))[:, None]     # gate order i, f, g, o: all but g halved
+            for c in range(H // 32):
+                rows = (n % 4) * H + 32 * c + n // 4
+                wx = np.zeros((64, kin_pad + 16), np.float32)
+                wx[:, : w_ih.shape[1]] = w_ih[rows] * scale
+                b_s = bias[rows] * scale[:, 0]
+                b_hi = b_s.astype(np.float16)
+                # the bias K step lives in the hi tile only: rows kin_pad (fp16(b)) and kin_pad + 1 (b - fp16(b))
+                ext = np.zeros((64, kin_pad + 16), np.float16)
+                ext[:, : kin_pad] = wx[:, : kin_pad].astype(np.float16)
+                ext[:, kin_pad] = b_hi
+                ext[:, kin_pad + 1] = (b_s - b_hi.astype(np.float32)).astype(np.float16)
+                p0 = np.ascontiguousarray(ext.reshape(64, (kin_pad + 16) // 8, 8).transpose(1, 0, 2)).view(np.uint8).ravel()
+                p1 = tiles(wx[:, : kin_pad])[1]
+                wh_hi, wh_lo = tiles(w_hh[rows] * scale)
+                parts += [p0, p1, wh_hi, wh_lo]
+    w_full = np.zeros((16, H), np.float32)
+    w_full[: min(O, 16)] = st["output_layer.weight"][:16]
+    for t in tiles(w_full):
+        parts.append(t)
+    return np.ascontiguousarray(np.concatenate(parts))
+
+
 def packed_floats(I, H, L, O):
     """Python mirror of ``ape_pack_total_floats`` (checked against the library in tests/test_cabi.py)."""
     kin0 = -(-I // N.KSLICE) * N.KSLICE

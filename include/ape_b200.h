@@ -141,7 +141,8 @@ typedef struct ape_lstm_args {
     int ws_E;
     /* tensor-core path, H = 128, L >= 3: how consecutive layers >= 1 are launched.  0 = automatic (a pair of layers runs as ONE
        two-layer wavefront launch, csrc/ape_lstm_tcw.cu, when the batch fills the GPU), 1 = one launch per layer always,
-       2 = wavefront pairs always */
+       2 = wavefront pairs always, 3 = the SPLIT-PRECISION variant (every operand an fp16 pair hi + lo, three tensor-core passes per
+       product, ex2 / rcp cell update: fp32-grade results at ~1/2 of the single-pass throughput; needs weights_tcx) */
     int tc_flags;
     /* fp32 path: optional initial state (h_0, c_0) of torch.nn.LSTM(x, hs) (nn_models.py:180-189): [L][E][H] float32 each, both
        or neither; needs n_samples == 1 (a caller with per-sample states passes the samples as estimates) */
@@ -152,6 +153,9 @@ typedef struct ape_lstm_args {
        few CTAs of stage 1 + layer 0 of the NEXT call (a high-priority side stream, ape_pipeline_submit) start at once instead of
        waiting for a persistent launch to retire CTAs; 0 = use every SM */
     int reserve_sms;
+    /* split-precision tensor-core variant (tc_flags == 3; csrc/ape_lstm_tcx.cu, H = 128): its weight blob, packed by
+       pack_lstm_weights_tcx() (ape_lstm_tcx_blob_bytes() bytes); the workspace must then hold ape_mc_lstm_tcx_workspace_bytes() */
+    const void* weights_tcx;
 } ape_lstm_args;
 
 int ape_mc_lstm_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
@@ -170,6 +174,10 @@ int ape_mc_lstm_tc_workspace_bytes(int I, int H, int L, int T, int O, int E, int
 /* workspace of a call with all_steps != 0 (keeps the last layer's sequence for the per-step output layer) */
 int ape_mc_lstm_tc_workspace_bytes_all_steps(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
 int ape_mc_lstm_tc(const ape_lstm_args* args, void* stream);
+/* split-precision variant (tc_flags == 3): supported shapes (H = 128, O <= 16, L >= 2), blob and workspace sizes */
+int ape_mc_lstm_tcx_supported(int I, int H, int L, int O);
+int ape_lstm_tcx_blob_bytes(int I, int H, int L, int64_t* bytes);
+int ape_mc_lstm_tcx_workspace_bytes(int I, int H, int L, int T, int O, int E, int n_samples, uint64_t* bytes);
 /* number of kernels ape_mc_lstm_tc launches for these arguments (layer pairs of an H = 128 model count once) */
 int ape_mc_lstm_tc_launch_count(const ape_lstm_args* args, int* launches);
 /*
