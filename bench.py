@@ -473,6 +473,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_other_models and args.workload == "uarm_1024x100":
         del be                                                # free its buffers before the other models are set up
         line["fp32_exact"] = fp32_exact_leg(BatchedEstimator, N, syn, torch, kind, B, n, smooth)
+        line["tc_split"] = tc_split_leg(BatchedEstimator, N, syn, torch, kind, B, n, smooth)
         line["other_models"] = {w: quick_throughput(w, args.lstm, BatchedEstimator, N, syn, torch, sustained_seconds=0 if args.no_sustained else 2.0)
                                 for w in ("watch_only_1024x100", "pocket_1024x100")}
     if rank == 0 and world == 1 and not args.no_realtime:
@@ -532,6 +533,59 @@ def fp32_exact_leg(BatchedEstimator, N, syn, torch, kind, B, n, smooth, steps=6)
                         "flops_per_launch": flops, "ms_per_launch": dom_ms, "layer_ms": [float(v) for v in acc]}}
     out["roofline"].update(ffma_peak_fields(N, torch, achieved))
     return out
+
+
+def tc_split_leg(BatchedEstimator, N, syn, torch, kind, B, n, smooth, steps=40, warmup=5):
+    """The split-precision tensor-core kernel (csrc/ape_lstm_tcx.cu: fp16 pairs hi + lo, three tcgen05 passes per product, ex2 / rcp
+    cell update) forced on the headline workload: what `auto` runs for an H = 128 model whose weights fail the single-pass probe,
+    instead of the fp32 FFMA kernel.  Device-resident and end to end; roofline = ALGORITHMIC flops of a layer >= 1 launch (the
+    kernel executes three times as many) against the burst tensor peak."""
+    be, spec = make_estimator(BatchedEstimator, N, syn, kind, B, n, smooth, "tcx")
+    I, H, L, T, O = (spec[k] for k in "IHLTO")
+    base = syn.synth_rows(kind, 64, steps + warmup, config_id=3)
+    rows = np.ascontiguousarray(np.tile(base, (B // 64, 1, 1)))
+    rows_dev = torch.from_numpy(rows).cuda()
+    frames = [rows_dev[:, f:f + 1].contiguous() for f in range(steps + warmup)]
+    time.sleep(0.5)
+    for f in range(warmup):
+        be.step_device(frames[f], raw_ready=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for f in range(warmup, warmup + steps):
+        be.step_device(frames[f], raw_ready=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    acc = layer_times(be, frames[warmup:], 3, L)
+    time.sleep(0.5)
+    be.reset()
+    for f in range(warmup):
+        be.step(rows[:, f:f + 1])
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    pending, checksum = [], 0.0
+    for f in range(warmup, warmup + steps):
+        pending.append(be.submit(rows[:, f:f + 1]))
+        if len(pending) >= be.N_SLOTS - 1:
+            checksum += float(pending.pop(0).result().msg[0, 0, 4])
+    for p in pending:
+        checksum += float(p.result().msg[0, 0, 4])
+    g1.record()
+    torch.cuda.synchronize()
+    e2e_ms = g0.elapsed_time(g1)
+    peaks, _ = measured_peaks()
+    flops = B * n * T * 2 * 4 * H * (2 * H)
+    dom_ms = float(np.mean(acc[1:]))
+    achieved = flops / (dom_ms * 1e-3) / 1e12
+    return {"value": B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "lstm_variant": "tcgen05_split_precision_fp16_pairs_3_passes", "probe_error_m": be.tcx_probe_error_m,
+            "e2e": {"value": B * steps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / steps, "checksum": checksum},
+            "roofline": {"bound": "tensor", "kernel": "lstm_layer_tcx_kernel (one layer >= 1 launch)", "achieved": achieved,
+                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                         "executed_frac": 3.0 * achieved / peaks["bf16_tflops"], "flops_per_launch": flops, "ms_per_launch": dom_ms,
+                         "layer_ms": [float(v) for v in acc],
+                         "note": "frac counts ALGORITHMIC flops (SURVEY.md §8d); the three passes per product execute 3x (+ the bias K step)"}}
 
 
 def relabel_leg(BatchedEstimator, N, syn, torch, dist, rank, world, lstm, max_over_ranks, barrier, R=1024, F=128, fpc=4):
