@@ -736,15 +736,6 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
         wl += tc_layer_bytes(l, g->I, H);
         if (l < l_begin) { ++l; continue; }
         const tc::TcLayerArgs a = layer_args(l, wl_l);
-        if (l == 0 && l0s::enabled() && l0s::supported(H, g->I, E)) {
-            // a handful of estimates (the single-stream real-time case): layer 0 is a recurrence over <= 8 rows - a cluster of 8 CTAs
-            // with resident fp32 weight slices instead of a full MMA tile per step (csrc/ape_lstm_l0s.cu)
-            rc = l0s::launch(g, units0, nullptr, a.out_scale, st);
-            if (rc != APE_OK) return rc;
-            if (prof) APE_CUDA_TRY(cudaEventRecord(ev[l + 1], st));
-            ++l;
-            continue;
-        }
         if (pair_ok && l >= 1 && l + 1 < l_end) {
             const tc::TcLayerArgs b = layer_args(l + 1, wl);
             wl += tc_layer_bytes(l + 1, g->I, H);

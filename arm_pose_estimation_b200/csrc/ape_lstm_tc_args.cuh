@@ -124,13 +124,6 @@ size_t scratch_bytes(int H, int sm_count);      // per-CTA cell-state scratch of
 int launch_pair(const tc::TcLayerArgs& a, const tc::TcLayerArgs& b, int sm_count, cudaStream_t st);
 }  // namespace tcw
 
-namespace l0s {
-// layer 0 of a small call (E <= 8 estimates) on a cluster of 8 CTAs with resident fp32 weight slices (ape_lstm_l0s.cu)
-bool supported(int H, int I, long long E);
-int launch(const ape_lstm_args* g, uint4* out_hi, uint4* out_lo, float out_scale, cudaStream_t st);
-bool enabled();                                 // false when APE_NO_L0S is set in the environment (A/B runs)
-}  // namespace l0s
-
 namespace tcx {
 // split-precision kernel (ape_lstm_tcx.cu): every operand an fp16 pair hi + lo, three tensor-core passes per product, ex2 / rcp cell
 bool supported(int H, int I, int O);

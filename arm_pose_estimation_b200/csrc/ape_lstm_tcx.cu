@@ -608,9 +608,7 @@ int run(const ape_lstm_args* g, cudaStream_t st) {
         a.pred_ring = g->pred_ring; a.n_out = g->n_samples;
         a.cstate = (float*)(scratch + (l == 0 ? 0 : wl.scratch));
         a.timeline = (g->trace && g->trace_layer < 0) ? (long long*)g->trace + (size_t)l * MAX_SMS * 4 : nullptr;
-        int rc;
-        if (l == 0 && l0s::enabled() && l0s::supported(H, g->I, E)) rc = l0s::launch(g, u0_hi, u0_lo, a.out_scale, st);   // (see ape_lstm_tc.cu)
-        else rc = launch_layer(a, l == 0 ? sm_count : sm_big, st);
+        const int rc = launch_layer(a, l == 0 ? sm_count : sm_big, st);
         if (rc != APE_OK) return rc;
         if (prof) APE_CUDA_TRY(cudaEventRecord(ev[l + 1], st));
     }
