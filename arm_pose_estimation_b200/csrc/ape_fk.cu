@@ -36,7 +36,12 @@ struct FkArgs {
     const float* est_in;      // FROM_EST: [E][S][W] rows of arm_pose_from_nn_targets instead of network targets
 };
 
-constexpr int FK_LANES = 16;                       // lanes per estimate
+#ifndef APE_FK_LANES
+#define APE_FK_LANES 16
+#endif
+constexpr int FK_LANES = APE_FK_LANES;             // lanes per estimate (fixes the summation order: never chosen by batch size)
+constexpr int FK_SUB = 32 / FK_LANES;              // estimates per warp
+static_assert(FK_LANES == 8 || FK_LANES == 16, "lanes per estimate");
 
 __device__ __forceinline__ float warp_sum(float v, unsigned m) {          // over the 16 lanes of this half-warp (mask m)
 #pragma unroll
@@ -65,7 +70,7 @@ template <int TARGET, bool FROM_EST>
 __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGET)) fk_reduce_kernel(FkArgs a) {
     constexpr int O = TARGET == APE_TARGET_ORI_CAL_LARM_UARM ? 12 : (TARGET == APE_TARGET_ORI_CAL_LARM_UARM_HIPS ? 14 : 20);
     constexpr int W = TARGET == APE_TARGET_ORI_CAL_LARM_UARM ? 14 : 21;
-    __shared__ float s_msg[FK_WARPS_PER_CTA * 2][32];
+    __shared__ float s_msg[FK_WARPS_PER_CTA * FK_SUB][32];
     __shared__ float s_m[O], s_s[O];
 
     if (threadIdx.x < O) {
@@ -74,10 +79,10 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGE
     }
     __syncthreads();
 
-    const int warp = threadIdx.x >> 5, half = (threadIdx.x >> 4) & 1, lane = threadIdx.x & (FK_LANES - 1);   // lane within the half-warp
-    const unsigned hm = 0xFFFFu << (16 * half);        // this half-warp's lanes: every shuffle / ballot below stays inside it
-    const int l0 = 16 * half;                          // its first lane
-    const int e = (blockIdx.x * FK_WARPS_PER_CTA + warp) * 2 + half;
+    const int warp = threadIdx.x >> 5, half = (threadIdx.x & 31) / FK_LANES, lane = threadIdx.x & (FK_LANES - 1);   // lane within the sub-warp
+    const unsigned hm = ((1u << FK_LANES) - 1u) << (FK_LANES * half);   // this sub-warp's lanes: every shuffle / ballot below stays inside it
+    const int l0 = FK_LANES * half;                    // its first lane
+    const int e = (blockIdx.x * FK_WARPS_PER_CTA + warp) * FK_SUB + half;
     const int E = a.B * a.nF;
     if (e >= E) return;
     const int b = e / a.nF;
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGE
     const unsigned any_bad = __ballot_sync(hm, bad) & hm;
 
     if (lane == 0) {
-        float* o = s_msg[warp * 2 + half];                                             // compose_msg.py:67-79 / :100-108
+        float* o = s_msg[warp * FK_SUB + half];                                             // compose_msg.py:67-79 / :100-108
         o[0] = m.larm.w; o[1] = m.larm.x; o[2] = m.larm.y; o[3] = m.larm.z;
         o[4] = m.hand.x; o[5] = m.hand.y; o[6] = m.hand.z;
         o[7] = m.larm.w; o[8] = m.larm.x; o[9] = m.larm.y; o[10] = m.larm.z;
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGE
         if (a.status) a.status[e] = any_bad ? 1 : 0;
     }
     __syncwarp(hm);
-    for (int k = lane; k < 25; k += FK_LANES) a.msg[(size_t)e * 25 + k] = s_msg[warp * 2 + half][k];
+    for (int k = lane; k < 25; k += FK_LANES) a.msg[(size_t)e * 25 + k] = s_msg[warp * FK_SUB + half][k];
     if (a.stdev && lane < 6) {
         float v = sd[0];
 #pragma unroll
@@ -273,7 +278,7 @@ extern "C" int ape_fk_reduce(const float* preds, int pred_ring, const float* yy_
     if (E == 0) return APE_OK;
     if (E > 0x7fffffffLL || (long long)smooth * n_samples > 0x7fffffffLL) return APE_ERR_BAD_ARG;
     FkArgs a{preds, pred_ring, yy_m, yy_s, body9, O, B, nF, frame0, n_samples, smooth, stream_frames, msg, samples, stdev, est_rows, status, nullptr};
-    const int grid = (int)((E + 2 * FK_WARPS_PER_CTA - 1) / (2 * FK_WARPS_PER_CTA));
+    const int grid = (int)((E + FK_SUB * FK_WARPS_PER_CTA - 1) / (FK_SUB * FK_WARPS_PER_CTA));
     cudaStream_t st = (cudaStream_t)stream;
     if (target == APE_TARGET_ORI_CAL_LARM_UARM)
         fk_reduce_kernel<APE_TARGET_ORI_CAL_LARM_UARM, false><<<grid, FK_WARPS_PER_CTA * 32, 0, st>>>(a);
@@ -292,7 +297,7 @@ extern "C" int ape_msg_from_est(const float* est, int W, const float* body9, int
     if (W != (target == APE_TARGET_ORI_CAL_LARM_UARM ? 14 : 21)) return APE_ERR_BAD_ARG;
     if (E == 0) return APE_OK;
     FkArgs a{nullptr, 1, nullptr, nullptr, body9, target_num_outputs(target), E, 1, 0, S, 1, nullptr, msg, nullptr, stdev, nullptr, nullptr, est};
-    const int grid = (E + 2 * FK_WARPS_PER_CTA - 1) / (2 * FK_WARPS_PER_CTA);
+    const int grid = (E + FK_SUB * FK_WARPS_PER_CTA - 1) / (FK_SUB * FK_WARPS_PER_CTA);
     cudaStream_t st = (cudaStream_t)stream;
     if (target == APE_TARGET_ORI_CAL_LARM_UARM)
         fk_reduce_kernel<APE_TARGET_ORI_CAL_LARM_UARM, true><<<grid, FK_WARPS_PER_CTA * 32, 0, st>>>(a);

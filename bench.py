@@ -474,6 +474,7 @@ def run_ours(args, rank, world, local_rank):
         del be                                                # free its buffers before the other models are set up
         line["fp32_exact"] = fp32_exact_leg(BatchedEstimator, N, syn, torch, kind, B, n, smooth)
         line["tc_split"] = tc_split_leg(BatchedEstimator, N, syn, torch, kind, B, n, smooth)
+        line["ff"] = ff_leg(N, torch)
         line["other_models"] = {w: quick_throughput(w, args.lstm, BatchedEstimator, N, syn, torch, sustained_seconds=0 if args.no_sustained else 2.0)
                                 for w in ("watch_only_1024x100", "pocket_1024x100")}
     if rank == 0 and world == 1 and not args.no_realtime:
@@ -586,6 +587,38 @@ def tc_split_leg(BatchedEstimator, N, syn, torch, kind, B, n, smooth, steps=40, 
                          "executed_frac": 3.0 * achieved / peaks["bf16_tflops"], "flops_per_launch": flops, "ms_per_launch": dom_ms,
                          "layer_ms": [float(v) for v in acc],
                          "note": "frac counts ALGORITHMIC flops (SURVEY.md §8d); the three passes per product execute 3x (+ the bias K step)"}}
+
+
+def ff_leg(N, torch, rows=1024, n=100, I=110, H=128, Lh=2, O=14, reps=20):
+    """The MC-dropout feed-forward regressor (DropoutFF2D of the reference, nn_models.py:317-370; SURVEY.md §8 f.2 - no deployed model uses
+    it): 1024 rows (streams) x 100 MC samples per launch of `ape_mc_ff`; algorithmic flops = hidden stack once per row + the output
+    layer per (row, sample), against the fp32 FMA peak measured in this run.  (One CTA per row; a variant that carried 8 rows per CTA
+    through the hidden stack measured 1.8x SLOWER - 128 CTAs of four active warps with one L2 load per FMA step - and was dropped.)"""
+    import ctypes
+    g = torch.Generator(device="cuda").manual_seed(5)
+    floats = I * H + H + Lh * (H * H + H) + O * H + O
+    blob = torch.randn(floats, generator=g, device="cuda") * 0.05
+    x = torch.randn((rows, I), generator=g, device="cuda")
+    preds = torch.empty((rows, n, O), device="cuda")
+    lib, st = N.load(), N.current_stream_ptr()
+
+    def run():
+        N.check(lib.ape_mc_ff(N.ptr(blob), I, H, Lh, O, 0.2, N.ptr(x), rows, n, N.MASK_PHILOX, None, 7, 0, 0, N.ptr(preds), st), "ape_mc_ff")
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = rows * 2 * (I * H + Lh * H * H) + rows * n * 2 * H * O
+    tf = flops / (ms * 1e-3) / 1e12
+    out = {"kernel": "mc_ff_kernel", "model": {"I": I, "H": H, "hidden_layers": Lh, "O": O}, "rows": rows, "mc_samples": n, "ms_per_launch": ms,
+           "value": rows / (ms * 1e-3), "unit": "rows x 100 MC samples per s", "achieved": tf, "flops_per_launch": flops}
+    out.update(ffma_peak_fields(N, torch, tf))
+    return out
 
 
 def relabel_leg(BatchedEstimator, N, syn, torch, dist, rank, world, lstm, max_over_ranks, barrier, R=1024, F=128, fpc=4):
