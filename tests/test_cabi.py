@@ -32,7 +32,11 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     # field order of struct ape_lstm_args in the header == ctypes Structure
     text = (ROOT / "include" / "ape_b200.h").read_text()
-    body = re.search(r"typedef struct ape_lstm_args \{(.*?)\} ape_lstm_args;", text, flags=re.S).group(1)
+    assert _struct_fields(text, "ape_lstm_args") == [f[0] for f in N.LstmArgs._fields_]
+
+
+def _struct_fields(text, name):
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = []
     for decl in body.split(";"):
@@ -40,8 +44,52 @@ def test_struct_layout_matches_header():
         if not decl:
             continue
         for part in decl.split(","):
-            names.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", part.strip())[0])
-    assert names == [f[0] for f in N.LstmArgs._fields_]
+            names.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*(?:\[[^\]]*\])?\s*$", part.strip())[0])
+    return names
+
+
+def test_pipeline_desc_layout_matches_header():
+    # struct ape_pipeline_desc (ABI 6) embeds ape_lstm_args by value: field order and the array extents must agree with ctypes
+    text = (ROOT / "include" / "ape_b200.h").read_text()
+    assert _struct_fields(text, "ape_pipeline_desc") == [f[0] for f in N.PipelineDesc._fields_]
+    assert int(re.search(r"#define APE_PIPELINE_MAX_SLOTS (\d+)", text).group(1)) == N.PIPELINE_MAX_SLOTS
+    flags = {k: int(v) for k, v in re.findall(r"#define (APE_PIPE_[A-Z0-9_]+) +(\d+)", text)}
+    assert flags == {"APE_PIPE_INPUT_PENDING": N.PIPE_INPUT_PENDING, "APE_PIPE_CALLER_WAITS": N.PIPE_CALLER_WAITS, "APE_PIPE_D2H": N.PIPE_D2H}
+    d = N.PipelineDesc()
+    assert ctypes.sizeof(d.out_dev) == 8 * N.PIPELINE_MAX_SLOTS and ctypes.sizeof(d.frames_dev) == 8 * 4
+    assert N.PipelineDesc.lstm.size == ctypes.sizeof(N.LstmArgs)
+    lib = N.load()
+    assert lib.ape_pipeline_create(None, None) == N.APE_ERR_BAD_ARG
+    assert lib.ape_pipeline_submit(None, None, None, 1, 0, None, 0, None, None) == N.APE_ERR_BAD_ARG
+    assert lib.ape_pipeline_destroy(None) == N.APE_OK
+
+
+def test_split_precision_blob_layout():
+    # pack_lstm_weights_tcx: per layer 2 CTAs x 4 chunks x [Wx_hi + bias K step | Wx_lo | Wh_hi | Wh_lo]; hi + lo reproduce the (halved)
+    # weights to ~2^-20, the bias rides in rows kin_pad / kin_pad + 1 of the hi tile, and the size matches the library's
+    import numpy as np
+    from arm_pose_estimation_b200 import synthetic as syn
+    I, H, L, O = 38, 128, 3, 12
+    state = syn.synth_state_dict(I, H, L, O, 3)
+    blob = nn_models.pack_lstm_weights_tcx(state)
+    assert blob.size == N.tcx_blob_bytes(I, H, L) and N.tcx_supported(I, H, L, O) and not N.tcx_supported(20, 256, 2, 12)
+    halfs = blob.view(np.float16)
+    kin_pad = 48
+    p0, p1, ph = (kin_pad + 16) * 64, kin_pad * 64, H * 64                # halfs per piece of layer 0
+    # layer 0, CTA 0, chunk 0: columns n = 4 u + g for units 0..15
+    hi = halfs[:p0].reshape((kin_pad + 16) // 8, 64, 8).transpose(1, 0, 2).reshape(64, kin_pad + 16).astype(np.float64)
+    lo = halfs[p0:p0 + p1].reshape(kin_pad // 8, 64, 8).transpose(1, 0, 2).reshape(64, kin_pad).astype(np.float64)
+    n = np.arange(64)
+    rows = (n % 4) * H + n // 4
+    scale = np.where(n % 4 != 2, 0.5, 1.0)
+    w = state["lstm.weight_ih_l0"][rows].astype(np.float64) * scale[:, None]
+    assert np.abs(hi[:, :I] + lo[:, :I] - w).max() <= 2.0 ** -20 * np.abs(w).max() and not hi[:, I:kin_pad].any()
+    b = (state["lstm.bias_ih_l0"] + state["lstm.bias_hh_l0"])[rows].astype(np.float64) * scale
+    assert np.abs(hi[:, kin_pad] + hi[:, kin_pad + 1] - b).max() <= 2.0 ** -20 * np.abs(b).max() and not hi[:, kin_pad + 2:].any()
+    wh_hi = halfs[p0 + p1:p0 + p1 + ph].reshape(H // 8, 64, 8).transpose(1, 0, 2).reshape(64, H).astype(np.float64)
+    wh_lo = halfs[p0 + p1 + ph:p0 + p1 + 2 * ph].reshape(H // 8, 64, 8).transpose(1, 0, 2).reshape(64, H).astype(np.float64)
+    wh = state["lstm.weight_hh_l0"][rows].astype(np.float64) * scale[:, None]
+    assert np.abs(wh_hi + wh_lo - wh).max() <= 2.0 ** -20 * np.abs(wh).max()
 
 
 def test_no_gpu_calls_fail_loudly_not_silently():
