@@ -618,6 +618,7 @@ extern "C" int ape_mc_lstm_tc_launch_count(const ape_lstm_args* g, int* launches
     const long long rows = (long long)g->B * g->nF * g->n_samples;
     const int l_begin = (g->layer_begin == 0 && g->layer_end == 0) ? 0 : g->layer_begin;
     const int l_end = (g->layer_begin == 0 && g->layer_end == 0) ? g->L : g->layer_end;
+    if (g->tc_flags == 4) { *launches = 1; return APE_OK; }
     const bool pair_ok = g->tc_flags != 3 && tc_pairs_layers(g, (rows + 255) / 256, sm_count);
     int n = 0;
     for (int l = l_begin; l < l_end;) { ++n; l += (pair_ok && l >= 1 && l + 1 < l_end) ? 2 : 1; }
@@ -661,7 +662,31 @@ extern "C" int ape_mc_lstm_tc(const ape_lstm_args* g, void* stream) {
     const int l_begin = (g->layer_begin == 0 && g->layer_end == 0) ? 0 : g->layer_begin;
     const int l_end = (g->layer_begin == 0 && g->layer_end == 0) ? g->L : g->layer_end;
     if (l_begin < 0 || l_end > g->L || l_begin >= l_end) return APE_ERR_BAD_ARG;
-    if (g->tc_flags < 0 || g->tc_flags > 2) return APE_ERR_BAD_ARG;
+    if (g->tc_flags < 0 || g->tc_flags > 4) return APE_ERR_BAD_ARG;
+    if (g->tc_flags == 4) {
+        // small-batch kernel: every layer of a call of <= 128 rows in ONE launch of one 8-CTA cluster (csrc/ape_lstm_tcl.cu)
+        if (l_begin != 0 || l_end != g->L || g->L > 4) return APE_ERR_UNSUPPORTED;
+        const uint8_t* lw[4] = {};
+        const float* lb[4] = {};
+        const uint8_t* p = (const uint8_t*)g->weights_tc;
+        for (int l = 0; l < g->L; ++l) {
+            lw[l] = p;
+            p += tc_layer_bytes(l, g->I, g->H);
+            lb[l] = (const float*)(p - (size_t)4 * g->H * 4);
+        }
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (g->layer_ms) { APE_CUDA_TRY(cudaEventCreate(&e0)); APE_CUDA_TRY(cudaEventCreate(&e1)); APE_CUDA_TRY(cudaEventRecord(e0, st)); }
+        rc = ape::tcl::run(g, lw, lb, p, wsp, st);
+        if (rc != APE_OK) return rc;
+        if (g->layer_ms) {                                  // the one launch is reported as layer 0's time
+            APE_CUDA_TRY(cudaEventRecord(e1, st));
+            APE_CUDA_TRY(cudaStreamSynchronize(st));
+            for (int l = 0; l < g->L; ++l) g->layer_ms[l] = 0.0f;
+            APE_CUDA_TRY(cudaEventElapsedTime(&g->layer_ms[0], e0, e1));
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
+        return APE_OK;
+    }
 
     cudaEvent_t ev[17] = {};
     const bool prof = g->layer_ms != nullptr && g->L <= 16 && l_begin == 0 && l_end == g->L;

@@ -124,6 +124,15 @@ size_t scratch_bytes(int H, int sm_count);      // per-CTA cell-state scratch of
 int launch_pair(const tc::TcLayerArgs& a, const tc::TcLayerArgs& b, int sm_count, cudaStream_t st);
 }  // namespace tcw
 
+namespace tcl {
+// small-batch kernel (ape_lstm_tcl.cu): all layers of a call of <= 128 rows in one launch of one cluster of 8 CTAs (hidden units split
+// across the cluster, h_t exchanged once per step)
+bool supported(int H, int I, int L, int O, long long E, int n);
+size_t workspace_bytes(int H, int T);
+int run(const ape_lstm_args* g, const uint8_t* const* layer_w, const float* const* layer_bias, const uint8_t* wo16, void* workspace,
+        cudaStream_t st);
+}  // namespace tcl
+
 namespace tcx {
 // split-precision kernel (ape_lstm_tcx.cu): every operand an fp16 pair hi + lo, three tensor-core passes per product, ex2 / rcp cell
 bool supported(int H, int I, int O);

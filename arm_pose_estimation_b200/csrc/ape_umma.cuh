@@ -239,6 +239,10 @@ __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// split form: a thread may arrive early and wait later (all threads of a warp together: .aligned)
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // ---- operand packing helpers ------------------------------------------------------------------------------------
 // byte offset of the 16-byte unit (row r, k-group j) in a tile of R rows
 __device__ __forceinline__ uint32_t unit_offset(int R, int r, int j) { return (uint32_t)(j * R + r) * 16u; }

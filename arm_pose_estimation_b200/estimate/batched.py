@@ -115,7 +115,7 @@ class BatchedEstimator:
                  smooth=1, dropout=0.2, bonemap=None, frames_per_call=1, emit_samples=True, normalize=True,
                  mask_mode=N.MASK_PHILOX, philox_seed=0, first_stream=0, device=None,
                  lstm_variant="auto", tc_min_rows=1, tc_tolerance_m=5e-5, pipeline=True, lanes=True, tc_flags=None,
-                 native_pipeline=None):
+                 native_pipeline=None, small_batch_kernel=True):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedEstimator needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = N.load()
@@ -200,6 +200,7 @@ class BatchedEstimator:
                 self.tc_weights = torch.from_numpy(nn_models.pack_lstm_weights_tc(state)).to(dev)
                 assert self.tc_weights.numel() == N.tc_blob_bytes(self.I, self.H, self.L)
                 ws_tc = N.workspace_bytes(self.I, self.H, self.L, self.T, self.O, B * nF, self.n, tensor_core=True) + 3 * 256 * self.T * self.H * 4
+                ws_tc += (2 + 2 * self.T) * (self.H // 8) * 2048 + 512          # (the small-batch kernel's exchange buffer and layer sequences)
                 if ws_tc > self.workspace.numel():
                     self.workspace = torch.empty(ws_tc, dtype=torch.uint8, device=dev)
                 self.tc_probe_error_m = self._probe_tc_error()
@@ -214,6 +215,14 @@ class BatchedEstimator:
                     ws_x = N.tcx_workspace_bytes(self.I, self.H, self.L, self.T, self.O, B * nF, self.n) + 1024
                     if ws_x > self.workspace.numel():
                         self.workspace = torch.empty(ws_x, dtype=torch.uint8, device=dev)
+            # A call of <= 128 rows (one stream x 100 MC samples: the real-time case) can run ALL layers in one launch of one 8-CTA cluster
+            # with the hidden units split across it (csrc/ape_lstm_tcl.cu) instead of one CTA pair walking every gate column of every
+            # layer.  Same operand rounding, accumulation order and Philox keys as the layer kernels: results are bit-identical
+            # (tests/test_gpu_tcl.py), so it is simply what such an estimator runs (small_batch_kernel=False: the layer kernels).
+            self.small_batch = (bool(small_batch_kernel) and self.lstm_variant == "tc" and not self.tc_split and self.tc_flags == 0
+                                and self.L <= 4 and self.H in (128, 256) and B * nF * self.n <= 128)
+            if self.small_batch:
+                self.tc_flags = 4
             # cross-call software pipeline (tensor-core path), two levels:
             #  * stage 1 + LSTM layer 0 of call k+1 (a few dozen CTAs) run on a side stream under call k's big layer kernels;
             #    layer 0's output is double-buffered by call parity;
@@ -221,7 +230,7 @@ class BatchedEstimator:
             #    of consecutive calls go to two alternating "lane" streams with a workspace each: a layer's last round of tiles
             #    fills only part of the GPU (400 tiles over 74 pairs = 5.4 rounds), and the pairs that finish early pick up the
             #    next call's layer instead of idling until the launch drains.  At most two calls are in flight.
-            self.pipeline = bool(pipeline) and self.lstm_variant == "tc"
+            self.pipeline = bool(pipeline) and self.lstm_variant == "tc" and not self.small_batch      # (one launch: nothing to overlap)
             # With the pipeline the persistent launches of the layers >= 1 leave ONE SM pair free for the side stream: stage 1 + layer 0
             # of the next calls (<= 8 CTAs) otherwise only get SMs in the ~50 us in which a big launch retires its CTAs, and a call
             # whose layer 0 misses that window stalls its lane.  Measured (uarm 1024 x 100, B200): 0 -> 2 reserved SMs: device-resident

@@ -765,7 +765,9 @@ def realtime_latency(BatchedEstimator, N, syn, frames=300):
                           mask_mode=N.MASK_PHILOX, philox_seed=7)
     rows = syn.synth_rows(kind, 1, frames + 20, config_id=2)
     out = {"workload": "watch+phone pocket LSTM estimator (I22 H256 L2 T6 O14), 1 stream x 100 MC samples, frame by frame",
-           "lstm_variant": be.lstm_variant, "frames": frames}
+           "lstm_variant": be.lstm_variant, "frames": frames,
+           "lstm_kernel": "lstm_small_kernel<256> (all layers in one launch of one 8-CTA cluster, hidden units split across it)" if be.small_batch
+           else "one launch per layer on one CTA pair"}
     for key, fn, what in (("", be.step_graph, "BatchedEstimator.step_graph (one CUDA-graph launch: H2D + 3 stages + D2H, then sync)"),
                           ("eager_", be.step, "BatchedEstimator.step (H2D + 3 stages + D2H enqueued call by call, then sync)")):
         be.reset()
@@ -777,6 +779,25 @@ def realtime_latency(BatchedEstimator, N, syn, frames=300):
         lat = np.asarray(lat[20:]) * 1e3
         out.update({key + "p50_ms": float(np.percentile(lat, 50)), key + "p99_ms": float(np.percentile(lat, 99)),
                     key + "timing": "host wall clock around " + what})
+    # device time of the LSTM stage alone, and the same frame through the layer kernels (one CTA pair per layer) for comparison
+    import torch
+    lm = np.zeros(spec["L"], np.float32)
+    dev = torch.from_numpy(np.ascontiguousarray(rows[:, :1])).cuda()
+    for _ in range(3):
+        be.step_device(dev, layer_ms=lm)
+    out["lstm_device_ms"] = float(lm.sum())
+    ref = BatchedEstimator(kind=kind, layout=spec["layout"], state=state, seq_len=spec["T"], y_targets=spec["y_targets"],
+                           stats=spec["stats"], n_streams=1, mc_samples=100, smooth=1, dropout=spec["p"], frames_per_call=1,
+                           mask_mode=N.MASK_PHILOX, philox_seed=7, small_batch_kernel=False)
+    lat = []
+    for f in range(frames + 20):
+        t0 = time.perf_counter()
+        ref.step_graph(rows[:, f:f + 1])
+        lat.append(time.perf_counter() - t0)
+    out["layer_kernels_p50_ms"] = float(np.percentile(np.asarray(lat[20:]) * 1e3, 50))
+    for _ in range(3):
+        ref.step_device(dev, layer_ms=lm)
+    out["layer_kernels_lstm_device_ms"] = float(lm.sum())
     return out
 
 
