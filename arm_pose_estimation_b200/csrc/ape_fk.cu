@@ -5,7 +5,7 @@
 // 6.25 passes of 16 lanes instead of 3.1 passes of 32, and every reduction instruction serves two estimates), lanes stride over the
 // S = smooth * n_samples rows (consecutive lanes read consecutive rows), reductions by shuffles inside the half-warp, results staged
 // through shared memory so the 25-float message leaves coalesced.
-#include "ape_fk.cuh"
+#include "ape_fk_x2.cuh"
 
 namespace ape {
 
@@ -13,7 +13,7 @@ namespace ape {
 // at 64 it spills 45 values per pass.  Measured on B200, 32 768 estimates x 100 rows: O = 12: 8 / 6 / 5 CTAs = 0.080 / 0.068 / 0.070 ms,
 // O = 14: 0.109 / 0.089 / 0.076 ms.
 #ifndef APE_FK_MIN_BLOCKS
-#define APE_FK_MIN_BLOCKS(TARGET) ((TARGET) == APE_TARGET_ORI_CAL_LARM_UARM ? 6 : 5)
+#define APE_FK_MIN_BLOCKS(TARGET) ((TARGET) == APE_TARGET_ORI_CAL_LARM_UARM ? 5 : 4)
 #endif
 #ifndef APE_FK_WARPS
 #define APE_FK_WARPS 4
@@ -39,18 +39,34 @@ struct FkArgs {
 #ifndef APE_FK_LANES
 #define APE_FK_LANES 16
 #endif
+// Prediction rows reach the arithmetic through a per-lane ring of APE_FK_STAGES shared-memory slots filled with cp.async (LDGSTS): a
+// lane's rows of the next APE_FK_STAGES - 1 passes are in flight while it works on the current one, and no register holds them (with
+// the next row prefetched into registers the kernel needed 113 registers to run without spills).  0: prefetch one pass ahead in registers.
+#ifndef APE_FK_STAGES
+#define APE_FK_STAGES 0
+#endif
+constexpr int FK_STAGES = APE_FK_STAGES;
 constexpr int FK_LANES = APE_FK_LANES;             // lanes per estimate (fixes the summation order: never chosen by batch size)
 constexpr int FK_SUB = 32 / FK_LANES;              // estimates per warp
 static_assert(FK_LANES == 8 || FK_LANES == 16, "lanes per estimate");
 
-__device__ __forceinline__ float warp_sum(float v, unsigned m) {          // over the 16 lanes of this half-warp (mask m)
+constexpr unsigned FK_FULL = 0xffffffffu;
+// Sums over the FK_LANES lanes of a sub-warp.  Every lane of the warp takes part (full mask: a plain SHFL.BFLY - with a sub-warp mask
+// the compiler wraps each shuffle in a MATCH / REDUX / VOTE convergence check, a fifth of the kernel's instructions); the xor
+// distances stay below FK_LANES, so the two estimates of a warp never mix.
+__device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
-    for (int o = FK_LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    for (int o = FK_LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FK_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ F2 warp_sum(F2 v) {
+#pragma unroll
+    for (int o = FK_LANES / 2; o > 0; o >>= 1) v = v + shfl_xor2(v, o);
     return v;
 }
 
-template <typename T> __device__ __forceinline__ Quat<T> bcast0(const Quat<T>& q, unsigned m, int l0) {   // from the half-warp's lane 0
-    return {__shfl_sync(m, q.w, l0), __shfl_sync(m, q.x, l0), __shfl_sync(m, q.y, l0), __shfl_sync(m, q.z, l0)};
+template <typename T> __device__ __forceinline__ Quat<T> bcast0(const Quat<T>& q, int l0) {   // from the sub-warp's lane 0
+    return {__shfl_sync(FK_FULL, q.w, l0), __shfl_sync(FK_FULL, q.x, l0), __shfl_sync(FK_FULL, q.y, l0), __shfl_sync(FK_FULL, q.z, l0)};
 }
 
 // accumulate q flipped onto the hemisphere of q0 (transformations.py:44-49)
@@ -59,10 +75,20 @@ __device__ __forceinline__ void acc_aligned(Quat<float>& s, const Quat<float>& q
     const float sg = d < 0.0f ? -1.0f : 1.0f;
     s.w += sg * q.w; s.x += sg * q.x; s.y += sg * q.y; s.z += sg * q.z;
 }
+__device__ __forceinline__ void acc_aligned(Quat2& s, const Quat2& q, const Quat2& q0) {          // lower and upper arm at once
+    const F2 d = fma2(q.w, q0.w, fma2(q.x, q0.x, fma2(q.y, q0.y, q.z * q0.z)));
+    const F2 sg = pk(lo(d) < 0.0f ? -1.0f : 1.0f, hi(d) < 0.0f ? -1.0f : 1.0f);
+    s.w = fma2(sg, q.w, s.w); s.x = fma2(sg, q.x, s.x); s.y = fma2(sg, q.y, s.y); s.z = fma2(sg, q.z, s.z);
+}
 
-__device__ __forceinline__ Quat<float> warp_sum_normalised(Quat<float> s, unsigned m) {
-    s.w = warp_sum(s.w, m); s.x = warp_sum(s.x, m); s.y = warp_sum(s.y, m); s.z = warp_sum(s.z, m);
+__device__ __forceinline__ Quat<float> warp_sum_normalised(Quat<float> s) {
+    s.w = warp_sum(s.w); s.x = warp_sum(s.x); s.y = warp_sum(s.y); s.z = warp_sum(s.z);
     const float inv = inv_sqrt(s.w * s.w + s.x * s.x + s.y * s.y + s.z * s.z);
+    return {s.w * inv, s.x * inv, s.y * inv, s.z * inv};
+}
+__device__ __forceinline__ Quat2 warp_sum_normalised(Quat2 s) {
+    s.w = warp_sum(s.w); s.x = warp_sum(s.x); s.y = warp_sum(s.y); s.z = warp_sum(s.z);
+    const F2 inv = rsq2(fma2(s.w, s.w, fma2(s.x, s.x, fma2(s.y, s.y, s.z * s.z))));
     return {s.w * inv, s.x * inv, s.y * inv, s.z * inv};
 }
 
@@ -70,8 +96,12 @@ template <int TARGET, bool FROM_EST>
 __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGET)) fk_reduce_kernel(FkArgs a) {
     constexpr int O = TARGET == APE_TARGET_ORI_CAL_LARM_UARM ? 12 : (TARGET == APE_TARGET_ORI_CAL_LARM_UARM_HIPS ? 14 : 20);
     constexpr int W = TARGET == APE_TARGET_ORI_CAL_LARM_UARM ? 14 : 21;
+    constexpr bool HIPS = TARGET != APE_TARGET_ORI_CAL_LARM_UARM;
+    constexpr bool POS = TARGET == APE_TARGET_ORI_POS_CAL_LARM_UARM_HIPS;
+    constexpr int OL = POS ? 3 : 0, OU = POS ? 12 : 6, OH = POS ? 18 : 12;      // first column of the lower-arm / upper-arm 6D, of the hips (sin, cos)
     __shared__ float s_msg[FK_WARPS_PER_CTA * FK_SUB][32];
-    __shared__ float s_m[O], s_s[O];
+    __shared__ __align__(16) float s_m[O], s_s[O];
+    __shared__ __align__(16) float s_rows[FK_STAGES > 0 && !FROM_EST ? FK_STAGES : 1][FK_STAGES > 0 && !FROM_EST ? FK_WARPS_PER_CTA * 32 : 1][O];
 
     if (threadIdx.x < O) {
         s_m[threadIdx.x] = a.yy_m ? a.yy_m[threadIdx.x] : 0.0f;
@@ -80,15 +110,21 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGE
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, half = (threadIdx.x & 31) / FK_LANES, lane = threadIdx.x & (FK_LANES - 1);   // lane within the sub-warp
-    const unsigned hm = ((1u << FK_LANES) - 1u) << (FK_LANES * half);   // this sub-warp's lanes: every shuffle / ballot below stays inside it
+    const unsigned hm = ((1u << FK_LANES) - 1u) << (FK_LANES * half);   // this sub-warp's lanes
     const int l0 = FK_LANES * half;                    // its first lane
     const int e = (blockIdx.x * FK_WARPS_PER_CTA + warp) * FK_SUB + half;
     const int E = a.B * a.nF;
-    if (e >= E) return;
-    const int b = e / a.nF;
-    const int fb = a.stream_frames ? a.stream_frames[b] : a.frame0;
-    if (fb < 0) return;                            // the stream has no new frame in this call: its outputs stay untouched
-    const int f = fb + e % a.nF;
+    // A sub-warp without an estimate (past the end, or a stream with no new frame in this call: its outputs stay untouched) stays in
+    // the warp as a passive participant of the full-mask shuffles; a warp without any estimate leaves.
+    bool dead = e >= E;
+    int b = 0, f = 0;
+    if (!dead) {
+        b = e / a.nF;
+        const int fb = a.stream_frames ? a.stream_frames[b] : a.frame0;
+        dead = fb < 0;
+        f = fb + e % a.nF;
+    }
+    if (__all_sync(FK_FULL, dead)) return;
     const int S = a.smooth * a.n;
 
     Body<float> body;
@@ -96,14 +132,19 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGE
     body.uarm_vec = {a.body9[3], a.body9[4], a.body9[5]};
     body.uarm_orig = {a.body9[6], a.body9[7], a.body9[8]};
     body.bones_along_x = bones_are_along_x(body);      // (the default skeleton: a uniform branch)
+    const F2 len = pk(body.larm_vec.x, body.uarm_vec.x), len2 = len + len;
 
-    Quat<float> q0l{}, q0u{}, q0h{}, sl{0, 0, 0, 0}, su{0, 0, 0, 0}, sh{0, 0, 0, 0};
-    float piv[6] = {0, 0, 0, 0, 0, 0}, d1[6] = {0, 0, 0, 0, 0, 0}, d2[6] = {0, 0, 0, 0, 0, 0};
-    float psum[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // ORI_POS target: plain means of hand / elbow / shoulder
+    const F2 zero2 = splat(0.0f);
+    Quat2 q0{zero2, zero2, zero2, zero2}, sq{zero2, zero2, zero2, zero2};          // lo: lower arm, hi: upper arm
+    Quat<float> q0h{}, sh{0, 0, 0, 0};
+    // hand / elbow positions as the three pairs the samples row stores: (hand.x, hand.y), (hand.z, elbow.x), (elbow.y, elbow.z)
+    F2 piv[3] = {zero2, zero2, zero2}, d1[3] = {zero2, zero2, zero2}, d2[3] = {zero2, zero2, zero2};
+    F2 psum[3] = {zero2, zero2, zero2};            // ORI_POS target: plain means of hand / elbow / shoulder
+    float pshl[3] = {0, 0, 0};
     float sh0[3] = {0, 0, 0};                      // shoulder of row 0 (S == 1: the message copies row 0)
     bool bad = false;
 
-    int rw = lane / a.n, rs = lane - rw * a.n;        // this lane's row i = rw * n + rs (window frame, MC sample), advanced by 16 per pass
+    int rw = lane / a.n, rs = lane - rw * a.n;        // the row this lane requests next: i = rw * n + rs (window frame, MC sample), advanced by FK_LANES per pass
     // first prediction row of window frame rw (frames clamp to frame 0, estimator.py:114-115; the ring slot costs an integer
     // division, so it is re-derived only when the lane moves on to the next window frame - not per row)
     auto frame_rows = [&](int w) {
@@ -111,136 +152,176 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGE
         fw = fw < 0 ? 0 : fw;
         return a.preds + ((size_t)b * a.pred_ring + (size_t)(fw % a.pred_ring)) * a.n * O;
     };
-    const float* wrows = FROM_EST ? nullptr : frame_rows(rw);
-    // The prediction row of the NEXT pass is requested before this pass's arithmetic (a lane reads 48 - 80 bytes per pass: with the
-    // load issued where it is consumed, a third of the kernel's warp-cycles were spent waiting for it)
+    const float* wrows = (FROM_EST || dead) ? nullptr : frame_rows(rw);
+    int ireq = lane;                                  // index of that row; >= S: nothing left to request
     float pre[O];
-    auto request = [&](const float* row) {
-        if (O % 4 == 0) {                                        // 48 / 80-byte rows: 16-byte loads
+    int st_req = 0, st_use = 0;                       // ring slots of the next request / the next row to be used
+    // request this lane's next row (registers: 16- or 8-byte loads; ring: one cp.async per 16 / 8 bytes, one group per pass - also an
+    // empty one, so that "all but the newest FK_STAGES - 1 groups have landed" always means "the row of this pass is there")
+    auto request = [&]() {
+        if (!dead && ireq < S) {
+            const float* row = wrows + rs * O;
+            if (FK_STAGES > 0) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_rows[st_req][threadIdx.x][0]);
+                if (O % 4 == 0) {
 #pragma unroll
-            for (int j = 0; j < O / 4; ++j) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(row) + j);
-                pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w;
+                    for (int j = 0; j < O / 4; ++j)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * j), "l"(row + 4 * j) : "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < O / 2; ++j)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8 * j), "l"(row + 2 * j) : "memory");
+                }
+            } else if (O % 4 == 0) {
+#pragma unroll
+                for (int j = 0; j < O / 4; ++j) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + j);
+                    pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < O / 2; ++j) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(row) + j);
+                    pre[2 * j] = v.x; pre[2 * j + 1] = v.y;
+                }
             }
-        } else {                                                 // 56-byte rows: 8-byte loads
-#pragma unroll
-            for (int j = 0; j < O / 2; ++j) {
-                const float2 v = __ldg(reinterpret_cast<const float2*>(row) + j);
-                pre[2 * j] = v.x; pre[2 * j + 1] = v.y;
-            }
-        }
-    };
-    if (!FROM_EST && lane < S) request(wrows + rs * O);
-    float2* smp = a.samples ? reinterpret_cast<float2*>(a.samples + ((size_t)e * S + lane) * 6) : nullptr;   // this lane's row of the pass
-    for (int i0 = 0; i0 < S; i0 += FK_LANES) {
-        const int i = i0 + lane;
-        const bool live = i < S;
-        RowPose<float> r;
-        r.larm = r.uarm = r.hips = {1.0f, 0.0f, 0.0f, 0.0f};
-        r.hand = r.elbow = r.shoulder = {0.0f, 0.0f, 0.0f};
-        if (live && FROM_EST) {                                      // compose_msg.py entry: rows already hold quats + origins
-            const float* src = a.est_in + ((size_t)e * S + i) * W;
-            int k = 0;
-            r.hand = {src[0], src[1], src[2]};
-            r.elbow = {src[3], src[4], src[5]};
-            k = 6;
-            if (W == 21) { r.shoulder = {src[6], src[7], src[8]}; k = 9; } else { r.shoulder = body.uarm_orig; }
-            r.larm = {src[k], src[k + 1], src[k + 2], src[k + 3]};
-            r.uarm = {src[k + 4], src[k + 5], src[k + 6], src[k + 7]};
-            if (W == 21) r.hips = {src[k + 8], src[k + 9], src[k + 10], src[k + 11]};
-        } else if (live) {
-            float p[O];
-#pragma unroll
-            for (int j = 0; j < O; ++j) p[j] = pre[j];
-            // advance to the next pass's row (no integer division per row) and request it
+            ireq += FK_LANES;
             rs += FK_LANES;
             if (rs >= a.n) {
                 do { rs -= a.n; ++rw; } while (rs >= a.n);
                 if (rw < a.smooth) wrows = frame_rows(rw);
             }
-            if (i + FK_LANES < S) request(wrows + rs * O);
-#pragma unroll
-            for (int j = 0; j < O; ++j) p[j] = fmaf(p[j], s_s[j], s_m[j]);     // estimator.py:108-109
-            bool rb = false;
-            r = row_pose<float>(TARGET, p, body, rb);
-            bad |= rb;
         }
-        if (i0 == 0) {                                               // row 0 anchors the sign alignment and the std pivot
-            q0l = bcast0(r.larm, hm, l0); q0u = bcast0(r.uarm, hm, l0); q0h = bcast0(r.hips, hm, l0);
-            const float pv[6] = {r.hand.x, r.hand.y, r.hand.z, r.elbow.x, r.elbow.y, r.elbow.z};
+        if (FK_STAGES > 0) {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            st_req = st_req + 1 == FK_STAGES ? 0 : st_req + 1;
+        }
+    };
+    if (!FROM_EST) {
 #pragma unroll
-            for (int j = 0; j < 6; ++j) piv[j] = __shfl_sync(hm, pv[j], l0);
-            sh0[0] = __shfl_sync(hm, r.shoulder.x, l0);
-            sh0[1] = __shfl_sync(hm, r.shoulder.y, l0);
-            sh0[2] = __shfl_sync(hm, r.shoulder.z, l0);
+        for (int k = 0; k < (FK_STAGES > 0 ? FK_STAGES - 1 : 1); ++k) request();
+    }
+    unsigned long long* smp = a.samples ? reinterpret_cast<unsigned long long*>(a.samples + ((size_t)e * S + lane) * 6) : nullptr;   // this lane's row of the pass
+    // this pass's row (a lane without a row keeps the values of its previous one: they are not accumulated)
+    Quat2 q{splat(1.0f), zero2, zero2, zero2};
+    Quat<float> hips{1.0f, 0.0f, 0.0f, 0.0f};
+    Vec3<float> shoulder{0.0f, 0.0f, 0.0f};
+    F2 P[3] = {zero2, zero2, zero2};
+    for (int i0 = 0; i0 < S; i0 += FK_LANES) {
+        const int i = i0 + lane;
+        const bool live = !dead && i < S;
+        if (FK_STAGES > 0 && !FROM_EST) {              // keep FK_STAGES - 1 rows in flight, then wait for this pass's row
+            request();
+            asm volatile("cp.async.wait_group %0;" ::"n"(FK_STAGES > 0 ? FK_STAGES - 1 : 0) : "memory");
+        }
+        if (live && FROM_EST) {                                      // compose_msg.py entry: rows already hold quats + origins
+            const float* src = a.est_in + ((size_t)e * S + i) * W;
+            P[0] = pk(src[0], src[1]); P[1] = pk(src[2], src[3]); P[2] = pk(src[4], src[5]);
+            int k = 6;
+            if (W == 21) { shoulder = {src[6], src[7], src[8]}; k = 9; } else { shoulder = body.uarm_orig; }
+            q = {pk(src[k], src[k + 4]), pk(src[k + 1], src[k + 5]), pk(src[k + 2], src[k + 6]), pk(src[k + 3], src[k + 7])};
+            if (W == 21) hips = {src[k + 8], src[k + 9], src[k + 10], src[k + 11]};
+        } else if (live) {
+            float p[O];
+            if (FK_STAGES > 0) {
+                const float* sr = &s_rows[st_use][threadIdx.x][0];
+#pragma unroll
+                for (int j = 0; j < O; ++j) p[j] = fmaf(sr[j], s_s[j], s_m[j]);   // estimator.py:108-109
+            } else {
+#pragma unroll
+                for (int j = 0; j < O; ++j) p[j] = fmaf(pre[j], s_s[j], s_m[j]);
+                request();
+            }
+            bool rb = false;
+            q = six_to_quat_x2(p + OL, p + OU, rb);                  // estimate_joints.py:20-92
+            bad |= rb;
+            if (HIPS) hips = hips_quat(p[OH], p[OH + 1]);
+            shoulder = HIPS ? qrot(hips, body.uarm_orig) : body.uarm_orig;
+            if (POS) {                                               // positions are network outputs
+                P[0] = pk(p[0], p[1]); P[1] = pk(p[2], p[9]); P[2] = pk(p[10], p[11]);
+            } else if (body.bones_along_x) {                         // shoulder -> elbow -> hand (estimate_joints.py:61-63 / :84-85)
+                F2 vx, vy, vz;
+                qrot_x2(q, len, len2, vx, vy, vz);
+                const float ex = hi(vx) + shoulder.x, ey = hi(vy) + shoulder.y, ez = hi(vz) + shoulder.z;
+                P[0] = pk(lo(vx) + ex, lo(vy) + ey); P[1] = pk(lo(vz) + ez, ex); P[2] = pk(ey, ez);
+            } else {
+                const Vec3<float> el = vadd(qrot(q_hi(q), body.uarm_vec), shoulder), ha = vadd(qrot(q_lo(q), body.larm_vec), el);
+                P[0] = pk(ha.x, ha.y); P[1] = pk(ha.z, el.x); P[2] = pk(el.y, el.z);
+            }
+        }
+        if (FK_STAGES > 0) st_use = st_use + 1 == FK_STAGES ? 0 : st_use + 1;
+        if (i0 == 0) {                                               // row 0 anchors the sign alignment and the std pivot
+            q0 = {shfl_idx2(q.w, l0), shfl_idx2(q.x, l0), shfl_idx2(q.y, l0), shfl_idx2(q.z, l0)};
+            if (HIPS) q0h = bcast0(hips, l0);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) piv[j] = shfl_idx2(P[j], l0);
+            sh0[0] = __shfl_sync(FK_FULL, shoulder.x, l0);
+            sh0[1] = __shfl_sync(FK_FULL, shoulder.y, l0);
+            sh0[2] = __shfl_sync(FK_FULL, shoulder.z, l0);
         }
         if (live) {
-            acc_aligned(sl, r.larm, q0l);
-            acc_aligned(su, r.uarm, q0u);
-            if (TARGET != APE_TARGET_ORI_CAL_LARM_UARM) acc_aligned(sh, r.hips, q0h);
-            const float pv[6] = {r.hand.x, r.hand.y, r.hand.z, r.elbow.x, r.elbow.y, r.elbow.z};
+            acc_aligned(sq, q, q0);
+            if (HIPS) acc_aligned(sh, hips, q0h);
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const float d = pv[j] - piv[j];
-                d1[j] += d;
-                d2[j] = fmaf(d, d, d2[j]);
+            for (int j = 0; j < 3; ++j) {
+                const F2 d = P[j] - piv[j];
+                d1[j] = d1[j] + d;
+                d2[j] = fma2(d, d, d2[j]);
             }
-            if (TARGET == APE_TARGET_ORI_POS_CAL_LARM_UARM_HIPS) {
+            if (POS) {
 #pragma unroll
-                for (int j = 0; j < 6; ++j) psum[j] += pv[j];
-                psum[6] += r.shoulder.x; psum[7] += r.shoulder.y; psum[8] += r.shoulder.z;
+                for (int j = 0; j < 3; ++j) psum[j] = psum[j] + P[j];
+                pshl[0] += shoulder.x; pshl[1] += shoulder.y; pshl[2] += shoulder.z;
             }
             if (smp) {
-                smp[0] = make_float2(pv[0], pv[1]);
-                smp[1] = make_float2(pv[2], pv[3]);
-                smp[2] = make_float2(pv[4], pv[5]);
+                smp[0] = P[0].v; smp[1] = P[1].v; smp[2] = P[2].v;
                 smp += FK_LANES * 3;
             }
             if (a.est_rows) {
                 float* dst = a.est_rows + ((size_t)e * S + i) * W;
                 int k = 0;
 #pragma unroll
-                for (int j = 0; j < 6; ++j) dst[k++] = pv[j];
-                if (W == 21) { dst[k++] = r.shoulder.x; dst[k++] = r.shoulder.y; dst[k++] = r.shoulder.z; }
-                dst[k++] = r.larm.w; dst[k++] = r.larm.x; dst[k++] = r.larm.y; dst[k++] = r.larm.z;
-                dst[k++] = r.uarm.w; dst[k++] = r.uarm.x; dst[k++] = r.uarm.y; dst[k++] = r.uarm.z;
-                if (W == 21) { dst[k++] = r.hips.w; dst[k++] = r.hips.x; dst[k++] = r.hips.y; dst[k++] = r.hips.z; }
+                for (int j = 0; j < 3; ++j) { dst[k++] = lo(P[j]); dst[k++] = hi(P[j]); }
+                if (W == 21) { dst[k++] = shoulder.x; dst[k++] = shoulder.y; dst[k++] = shoulder.z; }
+                dst[k++] = lo(q.w); dst[k++] = lo(q.x); dst[k++] = lo(q.y); dst[k++] = lo(q.z);
+                dst[k++] = hi(q.w); dst[k++] = hi(q.x); dst[k++] = hi(q.y); dst[k++] = hi(q.z);
+                if (W == 21) { dst[k++] = hips.w; dst[k++] = hips.x; dst[k++] = hips.y; dst[k++] = hips.z; }
             }
         }
     }
 
     // ---- reduction over the S rows --------------------------------------------------------------------
     RowPose<float> m;
-    m.larm = warp_sum_normalised(sl, hm);
-    m.uarm = warp_sum_normalised(su, hm);
-    m.hips = TARGET == APE_TARGET_ORI_CAL_LARM_UARM ? Quat<float>{1.0f, 0.0f, 0.0f, 0.0f} : warp_sum_normalised(sh, hm);
-    if (S == 1) {                                                             // copied, not re-normalised
-        m.larm = q0l; m.uarm = q0u;
-        if (TARGET != APE_TARGET_ORI_CAL_LARM_UARM) m.hips = q0h;
-    }
+    const Quat2 mq = S == 1 ? q0 : warp_sum_normalised(sq);                   // one row: copied, not re-normalised
+    m.larm = q_lo(mq);
+    m.uarm = q_hi(mq);
+    m.hips = !HIPS ? Quat<float>{1.0f, 0.0f, 0.0f, 0.0f} : (S == 1 ? q0h : warp_sum_normalised(sh));
     const float invS = 1.0f / (float)S;
-    if (TARGET == APE_TARGET_ORI_POS_CAL_LARM_UARM_HIPS) {
+    if (POS) {
 #pragma unroll
-        for (int j = 0; j < 9; ++j) psum[j] = warp_sum(psum[j], hm) * invS;       // compose_msg.py:27-29
-        m.hand = {psum[0], psum[1], psum[2]};
-        m.elbow = {psum[3], psum[4], psum[5]};
-        m.shoulder = {psum[6], psum[7], psum[8]};
+        for (int j = 0; j < 3; ++j) psum[j] = warp_sum(psum[j]) * splat(invS);    // compose_msg.py:27-29
+#pragma unroll
+        for (int j = 0; j < 3; ++j) pshl[j] = warp_sum(pshl[j]) * invS;
+        m.hand = {lo(psum[0]), hi(psum[0]), lo(psum[1])};
+        m.elbow = {hi(psum[1]), lo(psum[2]), hi(psum[2])};
+        m.shoulder = {pshl[0], pshl[1], pshl[2]};
     } else if (S > 1) {
         chain(TARGET, body, m);                                               // FK again from the means
     } else {                                                                  // one row: copied as is (compose_msg.py:62-66)
-        m.hand = {piv[0], piv[1], piv[2]};
-        m.elbow = {piv[3], piv[4], piv[5]};
+        m.hand = {lo(piv[0]), hi(piv[0]), lo(piv[1])};
+        m.elbow = {hi(piv[1]), lo(piv[2]), hi(piv[2])};
         m.shoulder = {sh0[0], sh0[1], sh0[2]};
     }
     float sd[6];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        const float m1 = warp_sum(d1[j], hm) * invS, m2 = warp_sum(d2[j], hm) * invS;
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd[j]) : "f"(fmaxf(m2 - m1 * m1, 0.0f)));
+    for (int j = 0; j < 3; ++j) {
+        const F2 m1 = warp_sum(d1[j]) * splat(invS), m2 = warp_sum(d2[j]) * splat(invS), var = fma2(-m1, m1, m2);
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd[2 * j]) : "f"(fmaxf(lo(var), 0.0f)));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd[2 * j + 1]) : "f"(fmaxf(hi(var), 0.0f)));
     }
-    const unsigned any_bad = __ballot_sync(hm, bad) & hm;
+    const unsigned any_bad = __ballot_sync(FK_FULL, bad) & hm;
 
-    if (lane == 0) {
+    if (lane == 0 && !dead) {
         float* o = s_msg[warp * FK_SUB + half];                                             // compose_msg.py:67-79 / :100-108
         o[0] = m.larm.w; o[1] = m.larm.x; o[2] = m.larm.y; o[3] = m.larm.z;
         o[4] = m.hand.x; o[5] = m.hand.y; o[6] = m.hand.z;
@@ -251,7 +332,8 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGE
         o[21] = m.hips.w; o[22] = m.hips.x; o[23] = m.hips.y; o[24] = m.hips.z;
         if (a.status) a.status[e] = any_bad ? 1 : 0;
     }
-    __syncwarp(hm);
+    __syncwarp();
+    if (dead) return;
     for (int k = lane; k < 25; k += FK_LANES) a.msg[(size_t)e * 25 + k] = s_msg[warp * FK_SUB + half][k];
     if (a.stdev && lane < 6) {
         float v = sd[0];
