@@ -36,16 +36,12 @@ struct FkArgs {
     const float* est_in;      // FROM_EST: [E][S][W] rows of arm_pose_from_nn_targets instead of network targets
 };
 
+#ifndef APE_FK_L2_PREFETCH
+#define APE_FK_L2_PREFETCH 1
+#endif
 #ifndef APE_FK_LANES
 #define APE_FK_LANES 16
 #endif
-// Prediction rows reach the arithmetic through a per-lane ring of APE_FK_STAGES shared-memory slots filled with cp.async (LDGSTS): a
-// lane's rows of the next APE_FK_STAGES - 1 passes are in flight while it works on the current one, and no register holds them (with
-// the next row prefetched into registers the kernel needed 113 registers to run without spills).  0: prefetch one pass ahead in registers.
-#ifndef APE_FK_STAGES
-#define APE_FK_STAGES 0
-#endif
-constexpr int FK_STAGES = APE_FK_STAGES;
 constexpr int FK_LANES = APE_FK_LANES;             // lanes per estimate (fixes the summation order: never chosen by batch size)
 constexpr int FK_SUB = 32 / FK_LANES;              // estimates per warp
 static_assert(FK_LANES == 8 || FK_LANES == 16, "lanes per estimate");
@@ -101,7 +97,6 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGE
     constexpr int OL = POS ? 3 : 0, OU = POS ? 12 : 6, OH = POS ? 18 : 12;      // first column of the lower-arm / upper-arm 6D, of the hips (sin, cos)
     __shared__ float s_msg[FK_WARPS_PER_CTA * FK_SUB][32];
     __shared__ __align__(16) float s_m[O], s_s[O];
-    __shared__ __align__(16) float s_rows[FK_STAGES > 0 && !FROM_EST ? FK_STAGES : 1][FK_STAGES > 0 && !FROM_EST ? FK_WARPS_PER_CTA * 32 : 1][O];
 
     if (threadIdx.x < O) {
         s_m[threadIdx.x] = a.yy_m ? a.yy_m[threadIdx.x] : 0.0f;
@@ -119,10 +114,10 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGE
     bool dead = e >= E;
     int b = 0, f = 0;
     if (!dead) {
-        b = e / a.nF;
+        b = a.nF == 1 ? e : e / a.nF;                  // (an integer division is ~20 instructions: the usual shapes go around them)
         const int fb = a.stream_frames ? a.stream_frames[b] : a.frame0;
         dead = fb < 0;
-        f = fb + e % a.nF;
+        f = fb + (e - b * a.nF);
     }
     if (__all_sync(FK_FULL, dead)) return;
     const int S = a.smooth * a.n;
@@ -144,99 +139,91 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGE
     float sh0[3] = {0, 0, 0};                      // shoulder of row 0 (S == 1: the message copies row 0)
     bool bad = false;
 
-    int rw = lane / a.n, rs = lane - rw * a.n;        // the row this lane requests next: i = rw * n + rs (window frame, MC sample), advanced by FK_LANES per pass
+    int rw = lane < a.n ? 0 : lane / a.n, rs = lane - rw * a.n;        // the row this lane requests next: i = rw * n + rs (window frame, MC sample), advanced by FK_LANES per pass
+    int ireq = lane;                                  // its index
     // first prediction row of window frame rw (frames clamp to frame 0, estimator.py:114-115; the ring slot costs an integer
     // division, so it is re-derived only when the lane moves on to the next window frame - not per row)
     auto frame_rows = [&](int w) {
         int fw = f - a.smooth + 1 + w;
         fw = fw < 0 ? 0 : fw;
-        return a.preds + ((size_t)b * a.pred_ring + (size_t)(fw % a.pred_ring)) * a.n * O;
+        return a.preds + ((size_t)b * a.pred_ring + (size_t)(fw < a.pred_ring ? fw : fw % a.pred_ring)) * a.n * O;
     };
-    const float* wrows = (FROM_EST || dead) ? nullptr : frame_rows(rw);
-    int ireq = lane;                                  // index of that row; >= S: nothing left to request
+    if (dead || lane >= S) { rw = 0; rs = 0; ireq = S; }          // no row of its own: reads row 0 (of the buffer, when there is no estimate)
+    const float* wrows = FROM_EST ? nullptr : (dead ? a.preds : frame_rows(rw));
+    // The prediction row of the NEXT pass is requested before this pass's arithmetic (a lane reads 48 - 80 bytes per pass: with the
+    // load issued where it is consumed, a third of the kernel's warp-cycles were spent waiting for it).  Loads and arithmetic are
+    // unconditional (no divergent region around them, no predicated register updates): a lane that has run out of rows reads its last
+    // row again, and only the sums and the stores ask whether the lane has a row in this pass.
     float pre[O];
-    int st_req = 0, st_use = 0;                       // ring slots of the next request / the next row to be used
-    // request this lane's next row (registers: 16- or 8-byte loads; ring: one cp.async per 16 / 8 bytes, one group per pass - also an
-    // empty one, so that "all but the newest FK_STAGES - 1 groups have landed" always means "the row of this pass is there")
     auto request = [&]() {
-        if (!dead && ireq < S) {
-            const float* row = wrows + rs * O;
-            if (FK_STAGES > 0) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_rows[st_req][threadIdx.x][0]);
-                if (O % 4 == 0) {
+        const float* row = wrows + rs * O;
+        if (O % 4 == 0) {                                        // 48 / 80-byte rows: 16-byte loads
 #pragma unroll
-                    for (int j = 0; j < O / 4; ++j)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * j), "l"(row + 4 * j) : "memory");
-                } else {
-#pragma unroll
-                    for (int j = 0; j < O / 2; ++j)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8 * j), "l"(row + 2 * j) : "memory");
-                }
-            } else if (O % 4 == 0) {
-#pragma unroll
-                for (int j = 0; j < O / 4; ++j) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + j);
-                    pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < O / 2; ++j) {
-                    const float2 v = __ldg(reinterpret_cast<const float2*>(row) + j);
-                    pre[2 * j] = v.x; pre[2 * j + 1] = v.y;
-                }
+            for (int j = 0; j < O / 4; ++j) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(row) + j);
+                pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w;
             }
+        } else {                                                 // 56-byte rows: 8-byte loads
+#pragma unroll
+            for (int j = 0; j < O / 2; ++j) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(row) + j);
+                pre[2 * j] = v.x; pre[2 * j + 1] = v.y;
+            }
+        }
+        if (ireq + FK_LANES < S) {                               // (the last row is simply read again by the passes that have none)
             ireq += FK_LANES;
             rs += FK_LANES;
             if (rs >= a.n) {
                 do { rs -= a.n; ++rw; } while (rs >= a.n);
-                if (rw < a.smooth) wrows = frame_rows(rw);
+                wrows = frame_rows(rw);
             }
-        }
-        if (FK_STAGES > 0) {
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            st_req = st_req + 1 == FK_STAGES ? 0 : st_req + 1;
         }
     };
     if (!FROM_EST) {
-#pragma unroll
-        for (int k = 0; k < (FK_STAGES > 0 ? FK_STAGES - 1 : 1); ++k) request();
+        request();
+#if APE_FK_L2_PREFETCH
+        // ... and ALL rows of the estimate are asked into the L2 right away: one bulk prefetch per window frame (its n rows are
+        // contiguous), issued by lane w for frame w.  The register prefetch above then sees the L2's latency instead of the DRAM's from
+        // the second pass on (one pass of look-ahead is about 0.7 us of work per SM quarter - less than a loaded DRAM round trip).
+        const unsigned fbytes = (unsigned)a.n * O * 4u;
+        if (!dead && fbytes % 16u == 0) {
+            for (int w = lane; w < a.smooth; w += FK_LANES) {
+                const float* fr = frame_rows(w);
+                if ((reinterpret_cast<uintptr_t>(fr) & 15) == 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fr), "r"(fbytes) : "memory");
+            }
+        }
+#endif
     }
     unsigned long long* smp = a.samples ? reinterpret_cast<unsigned long long*>(a.samples + ((size_t)e * S + lane) * 6) : nullptr;   // this lane's row of the pass
-    // this pass's row (a lane without a row keeps the values of its previous one: they are not accumulated)
     Quat2 q{splat(1.0f), zero2, zero2, zero2};
     Quat<float> hips{1.0f, 0.0f, 0.0f, 0.0f};
-    Vec3<float> shoulder{0.0f, 0.0f, 0.0f};
+    Vec3<float> shoulder = body.uarm_orig;
     F2 P[3] = {zero2, zero2, zero2};
     for (int i0 = 0; i0 < S; i0 += FK_LANES) {
         const int i = i0 + lane;
         const bool live = !dead && i < S;
-        if (FK_STAGES > 0 && !FROM_EST) {              // keep FK_STAGES - 1 rows in flight, then wait for this pass's row
-            request();
-            asm volatile("cp.async.wait_group %0;" ::"n"(FK_STAGES > 0 ? FK_STAGES - 1 : 0) : "memory");
-        }
-        if (live && FROM_EST) {                                      // compose_msg.py entry: rows already hold quats + origins
-            const float* src = a.est_in + ((size_t)e * S + i) * W;
-            P[0] = pk(src[0], src[1]); P[1] = pk(src[2], src[3]); P[2] = pk(src[4], src[5]);
-            int k = 6;
-            if (W == 21) { shoulder = {src[6], src[7], src[8]}; k = 9; } else { shoulder = body.uarm_orig; }
-            q = {pk(src[k], src[k + 4]), pk(src[k + 1], src[k + 5]), pk(src[k + 2], src[k + 6]), pk(src[k + 3], src[k + 7])};
-            if (W == 21) hips = {src[k + 8], src[k + 9], src[k + 10], src[k + 11]};
-        } else if (live) {
-            float p[O];
-            if (FK_STAGES > 0) {
-                const float* sr = &s_rows[st_use][threadIdx.x][0];
-#pragma unroll
-                for (int j = 0; j < O; ++j) p[j] = fmaf(sr[j], s_s[j], s_m[j]);   // estimator.py:108-109
-            } else {
-#pragma unroll
-                for (int j = 0; j < O; ++j) p[j] = fmaf(pre[j], s_s[j], s_m[j]);
-                request();
+        if (FROM_EST) {                                              // compose_msg.py entry: rows already hold quats + origins
+            if (live) {
+                const float* src = a.est_in + ((size_t)e * S + i) * W;
+                P[0] = pk(src[0], src[1]); P[1] = pk(src[2], src[3]); P[2] = pk(src[4], src[5]);
+                int k = 6;
+                if (W == 21) { shoulder = {src[6], src[7], src[8]}; k = 9; }
+                q = {pk(src[k], src[k + 4]), pk(src[k + 1], src[k + 5]), pk(src[k + 2], src[k + 6]), pk(src[k + 3], src[k + 7])};
+                if (W == 21) hips = {src[k + 8], src[k + 9], src[k + 10], src[k + 11]};
             }
+        } else {
+            float p[O];
+#pragma unroll
+            for (int j = 0; j < O; ++j) p[j] = fmaf(pre[j], s_s[j], s_m[j]);   // estimator.py:108-109
+            request();
             bool rb = false;
             q = six_to_quat_x2(p + OL, p + OU, rb);                  // estimate_joints.py:20-92
-            bad |= rb;
-            if (HIPS) hips = hips_quat(p[OH], p[OH + 1]);
-            shoulder = HIPS ? qrot(hips, body.uarm_orig) : body.uarm_orig;
+            bad |= rb && live;
+            if (HIPS) {
+                hips = hips_quat(p[OH], p[OH + 1]);
+                shoulder = qrot(hips, body.uarm_orig);
+            }
             if (POS) {                                               // positions are network outputs
                 P[0] = pk(p[0], p[1]); P[1] = pk(p[2], p[9]); P[2] = pk(p[10], p[11]);
             } else if (body.bones_along_x) {                         // shoulder -> elbow -> hand (estimate_joints.py:61-63 / :84-85)
@@ -249,7 +236,6 @@ __global__ void __launch_bounds__(FK_WARPS_PER_CTA * 32, APE_FK_MIN_BLOCKS(TARGE
                 P[0] = pk(ha.x, ha.y); P[1] = pk(ha.z, el.x); P[2] = pk(el.y, el.z);
             }
         }
-        if (FK_STAGES > 0) st_use = st_use + 1 == FK_STAGES ? 0 : st_use + 1;
         if (i0 == 0) {                                               // row 0 anchors the sign alignment and the std pivot
             q0 = {shfl_idx2(q.w, l0), shfl_idx2(q.x, l0), shfl_idx2(q.y, l0), shfl_idx2(q.z, l0)};
             if (HIPS) q0h = bcast0(hips, l0);
