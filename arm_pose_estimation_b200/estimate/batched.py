@@ -107,6 +107,11 @@ class PendingEstimate:
         return EstimateBatch(msg, std, samples, status, self.frame0)
 
 
+class _GraphCall:
+    """State of the captured single-call graph (``BatchedEstimator.step_graph``): the graph, numpy views of its pinned staging
+    block (frame counters + rows) and of its pinned result block."""
+
+
 class BatchedEstimator:
     N_SLOTS = int(os.environ.get("APE_N_SLOTS", "8"))      # staging / result buffer sets: up to N_SLOTS - 1 submitted calls may be outstanding while the next is staged
                      # (measured end to end, uarm 1024 x 100: 3 outstanding 0.413 ms/step, 5 outstanding 0.392, 7 outstanding 0.391)
@@ -176,6 +181,7 @@ class BatchedEstimator:
             self.raw_host = [torch.zeros((B, nF, self.ncols), dtype=f32).pin_memory() for _ in range(NS)]
             self.out_host = [torch.zeros(n_words, dtype=f32).pin_memory() for _ in range(NS)]
             self.slot_event = [None] * NS
+            self._g, self._g_stale = None, False           # captured single-call graph; stale: other calls were enqueued since its last replay
             self.frames_host = self.frames_dev = None      # per-stream frame counters (multi-stream front-end), made on first use
             self.submits = 0
             # ---- which LSTM kernel: fp32 FFMA (exact) or tcgen05 fp16-operand tensor cores ----------------------
@@ -372,6 +378,15 @@ class BatchedEstimator:
         self.status = self.out_all[E * 31: E * 32].view(torch.int32).view(B, nF)
         self.samples = self.out_all[E * 32:].view(B, nF, self.S, 6) if self.emit_samples else None
 
+    def _use_out_mapped(self, host):
+        """Point the result views at a PINNED HOST block of the same layout (zero-copy results of the CUDA-graph path: pinned memory
+        is mapped into the device's address space under unified addressing, the kernels take its address like a device pointer)."""
+        B, nF, E = self.B, self.nF_max, self.B * self.nF_max
+        self.msg = host[: E * 25].view(B, nF, 25)
+        self.std = host[E * 25: E * 31].view(B, nF, 6)
+        self.status = host[E * 31: E * 32].view(torch.int32).view(B, nF)
+        self.samples = host[E * 32:].view(B, nF, self.S, 6) if self.emit_samples else None
+
     def reset(self):
         """Forget all history, like ``Estimator.reset`` (estimator.py:88-91): the next row is frame 0 again."""
         self.frame = 0
@@ -444,6 +459,7 @@ class BatchedEstimator:
         tensor ``[B]`` of per-stream absolute frame numbers for streams that do not advance in lock-step (a negative entry
         skips the stream in this call: its rings and outputs stay untouched); the shared frame counter is then not used."""
         nF = int(raw.shape[1]) if n_frames is None else int(n_frames)
+        self._g_stale = self._g_stale or not _plain
         if raw.shape[0] != self.B or nF > self.nF_max or raw.shape[2] != self.ncols or not raw.is_contiguous():
             raise UserWarning(f"raw rows must be a contiguous [B={self.B}, nF<={self.nF_max}, {self.ncols}] tensor, got {tuple(raw.shape)}")
         if raw.dtype != torch.float32:
@@ -565,6 +581,7 @@ class BatchedEstimator:
         nF = rows.shape[1]
         if rows.shape[0] != self.B or nF > self.nF_max or rows.shape[2] != self.ncols:
             raise UserWarning(f"rows must be [B={self.B}, nF<={self.nF_max}, {self.ncols}], got {rows.shape}")
+        self._g_stale = True
         if self._pipe is not None and masks is None:
             rows = np.ascontiguousarray(rows)
             sf = None if stream_frames is None else np.ascontiguousarray(np.asarray(stream_frames, dtype=np.int32).reshape(self.B))
@@ -613,71 +630,89 @@ class BatchedEstimator:
 
     # ---- single-call latency path: the whole call as one captured CUDA graph ------------------------------------
     def step_graph(self, rows, stream_frames=None):
-        """``step`` for the latency-bound case (a few streams, one call at a time - BASELINE configs[1]): pinned H2D of the rows
-        and of the frame counter, the three stages and the pinned D2H are captured ONCE as a CUDA graph and replayed with one
-        launch per call, so the host pays one ``cudaGraphLaunch`` instead of two copies and five kernel launches through Python.
-        The frame number reaches the kernels through the per-stream frame counters (a device array the graph refreshes from
-        pinned memory), so the captured kernel arguments never change.  Same kernels, same Philox keys: bit-equal to ``step``.
+        """``step`` for the latency-bound case (a few streams, one call at a time - BASELINE configs[1]): the whole call is captured
+        ONCE as a CUDA graph and replayed with one launch per frame.  The graph has four nodes: ONE pinned H2D copy (the per-stream
+        frame counters and the rows share a staging block, so the frame number reaches the kernels through device memory and the
+        captured kernel arguments never change) and the three stages; stage 3 writes the messages, std and samples STRAIGHT into
+        pinned host memory (mapped into the device's address space), so there is no D2H node.  Per frame the host does two small
+        numpy copies, one ``cudaGraphLaunch`` and one stream synchronize.  Same kernels, same Philox keys: bit-equal to ``step``.
         ``stream_frames``: optional host int32 ``[B]`` of per-stream frame numbers (negative: no new row), as in ``submit``."""
         rows = np.asarray(rows, dtype=np.float32)
         if rows.ndim == 2:
             rows = rows[:, None, :]
         nF = rows.shape[1]
+        g = self._g
+        if g is None or g.nF != nF or self._g_stale or torch.cuda.current_device() != g.dev_index:
+            g = self._graph_setup(rows, nF)                   # validates the shape, drains earlier pipelined calls, (re)captures
+        g.frames_np[...] = self.frame if stream_frames is None else np.asarray(stream_frames, dtype=np.int32).reshape(self.B)
+        g.rows_np[...] = rows
+        g.graph.replay()
+        torch.cuda.current_stream().synchronize()
+        out = EstimateBatch(g.msg, g.std, g.samples, g.status, self.frame)
+        self.frame += nF
+        self.calls += 1
+        self.launches += g.launches
+        return out
+
+    def _graph_setup(self, rows, nF):
+        """Slow path of ``step_graph`` (first call, another call size, or pipelined calls were submitted in between)."""
         if rows.shape[0] != self.B or nF > self.nF_max or rows.shape[2] != self.ncols:
             raise UserWarning(f"rows must be [B={self.B}, nF<={self.nF_max}, {self.ncols}], got {rows.shape}")
         with torch.cuda.device(self.device):
             self._leave_native()
-            for ev in self.slot_event:                       # nothing submitted earlier may still be using the staging slots
+            for ev in self.slot_event:                       # nothing submitted earlier may still be using the rings / the workspace
                 if ev is not None:
                     ev.synchronize()
-            E = self.B * nF
-            if getattr(self, "_graph_frames_host", None) is None:
-                self._graph_frames_host = torch.zeros(self.B, dtype=torch.int32).pin_memory()
-                self._graph_frames_dev = torch.zeros(self.B, dtype=torch.int32, device=self.device)
-                self._graph = None
-            self.raw_host[0].view(-1)[: E * self.ncols].view(self.B, nF, self.ncols).numpy()[...] = rows
-            self._graph_frames_host.numpy()[...] = self.frame if stream_frames is None else np.asarray(stream_frames, dtype=np.int32).reshape(self.B)
-            if self._graph is None or self._graph_nF != nF:
-                self._capture_graph(nF)                     # (its eager pass computes THIS call; the replay below repeats it)
-            self._graph.replay()
             torch.cuda.current_stream().synchronize()
-        msg, std, samples, status = self._host_views(0, nF)
-        out = EstimateBatch(msg, std, samples, status, self.frame)
-        self.frame += nF
-        self.calls += 1
-        self.launches += 2 + self._graph_lstm_launches
-        return out
+            self._g_stale = False
+            g = self._g
+            if g is None or g.nF != nF or torch.cuda.current_device() != g.dev_index:
+                g = self._capture_graph(rows, nF)
+        return g
 
-    def _capture_graph(self, nF):
-        E = self.B * nF
-        torch.cuda.current_stream().synchronize()
-        stage = self.raw_host[0].view(-1)[: E * self.ncols].view(self.B, nF, self.ncols)
-        raw = self.raw.view(-1)[: E * self.ncols].view(self.B, nF, self.ncols)
-        self._use_out(0)
-        host, dev_out = self.out_host[0], self.out_all
+    def _capture_graph(self, rows, nF):
+        B, E, Em = self.B, self.B * nF, self.B * self.nF_max
+        g = _GraphCall()
+        g.nF, g.dev_index = nF, torch.cuda.current_device()
+        fb = (B * 4 + 15) // 16 * 16                         # the frame counters first, the rows behind them (16-byte aligned)
+        stage_host = torch.zeros(fb + E * self.ncols * 4, dtype=torch.uint8).pin_memory()
+        stage_dev = torch.zeros(fb + E * self.ncols * 4, dtype=torch.uint8, device=self.device)
+        g.frames_np = stage_host[: B * 4].view(torch.int32).numpy()
+        g.rows_np = stage_host[fb:].view(torch.float32).view(B, nF, self.ncols).numpy()
+        raw, sf = stage_dev[fb:].view(torch.float32).view(B, nF, self.ncols), stage_dev[: B * 4].view(torch.int32)
+        # results: a pinned block of the device buffers' layout, written by the stage-3 kernel itself
+        out_host = torch.zeros(self.out_bufs[0].numel(), dtype=torch.float32).pin_memory()
+        host = out_host.numpy()
+        g.msg = host[: E * 25].reshape(B, nF, 25)
+        g.std = host[Em * 25: Em * 25 + E * 6].reshape(B, nF, 6)
+        g.status = host[Em * 31: Em * 31 + E].view(np.int32).reshape(B, nF)
+        g.samples = host[Em * 32: Em * 32 + E * self.S * 6].reshape(B, nF, self.S, 6) if self.emit_samples else None
+        g.keep = (stage_host, stage_dev, out_host)
+        # the first use stages THIS call before the eager pass below (the replay that follows repeats it with the same inputs and keys)
+        g.frames_np[...] = self.frame
+        g.rows_np[...] = rows
         saved = (self.frame, self.calls, self.launches)
 
         def enqueue():
-            self.step_device(raw, nF, _h2d_from=stage, stream_frames=self._graph_frames_dev, _frames_from=self._graph_frames_host,
-                             _out_slot=0, _plain=True)
-            if nF == self.nF_max:
-                host.copy_(dev_out, non_blocking=True)
-            else:
-                Em = self.B * self.nF_max
-                for off, width in ((0, 25), (Em * 25, 6), (Em * 31, 1)) + (((Em * 32, self.S * 6),) if self.emit_samples else ()):
-                    host[off: off + E * width].copy_(dev_out[off: off + E * width], non_blocking=True)
+            stage_dev.copy_(stage_host, non_blocking=True)
+            self._use_out_mapped(out_host)
+            try:
+                self._step_device(raw, nF, stream_frames=sf, _plain=True)
+            finally:
+                self._use_out(0)
 
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                        # one eager pass first (function attributes, lazy module loading): it
-            enqueue()                                        # computes the call that is already staged, and the replay that
-        side.synchronize()                                   # follows repeats it with the same inputs and Philox keys
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph, stream=side):
+        with torch.cuda.stream(side):                        # one eager pass first (function attributes, lazy module loading)
             enqueue()
-        self._graph_nF = nF
-        self._graph_lstm_launches = (self.launches - saved[2]) // 2 - 2      # (the eager pass and the capture each counted one call)
+        side.synchronize()
+        g.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g.graph, stream=side):
+            enqueue()
+        g.launches = (self.launches - saved[2]) // 2          # (the eager pass and the capture each counted one call)
         self.frame, self.calls, self.launches = saved
+        self._g = g
+        return g
 
     def _host_views(self, slot, nF):
         host, E, Em = self.out_host[slot].numpy(), self.B * nF, self.B * self.nF_max

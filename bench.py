@@ -768,7 +768,7 @@ def realtime_latency(BatchedEstimator, N, syn, frames=300):
            "lstm_variant": be.lstm_variant, "frames": frames,
            "lstm_kernel": "lstm_small_kernel<256> (all layers in one launch of one 8-CTA cluster, hidden units split across it)" if be.small_batch
            else "one launch per layer on one CTA pair"}
-    for key, fn, what in (("", be.step_graph, "BatchedEstimator.step_graph (one CUDA-graph launch: H2D + 3 stages + D2H, then sync)"),
+    for key, fn, what in (("", be.step_graph, "BatchedEstimator.step_graph (one CUDA-graph launch of 4 nodes: one pinned H2D copy of frame counter + row, the 3 stages, stage 3 writing its results straight into mapped pinned host memory; then sync)"),
                           ("eager_", be.step, "BatchedEstimator.step (H2D + 3 stages + D2H enqueued call by call, then sync)")):
         be.reset()
         lat = []
