@@ -6,23 +6,11 @@
 // slots for the same arithmetic (each half is the IEEE operation the scalar code of ape_fk.cuh does; only where a product and a sum fuse
 // into an FMA may the last bit differ from it).
 #pragma once
+#include "ape_f32x2.cuh"
 #include "ape_fk.cuh"
 
 namespace ape {
 
-struct F2 { unsigned long long v; };
-
-__device__ __forceinline__ F2 pk(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ F2 splat(float x) { return pk(x, x); }
-__device__ __forceinline__ float lo(F2 a) { return __uint_as_float((unsigned)a.v); }            // the pair's registers: no instruction
-__device__ __forceinline__ float hi(F2 a) { return __uint_as_float((unsigned)(a.v >> 32)); }
-__device__ __forceinline__ F2 operator+(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ F2 operator-(F2 a, F2 b) { F2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ F2 operator*(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ F2 operator-(F2 a) { return pk(-lo(a), -hi(a)); }          // folded into the consumer's operand modifier
-__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
-    F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r;
-}
 __device__ __forceinline__ F2 rsq2(F2 a) { return pk(inv_sqrt(lo(a)), inv_sqrt(hi(a))); }      // two MUFU.RSQ
 __device__ __forceinline__ F2 shfl_xor2(F2 a, int o) { return pk(__shfl_xor_sync(0xffffffffu, lo(a), o), __shfl_xor_sync(0xffffffffu, hi(a), o)); }
 __device__ __forceinline__ F2 shfl_idx2(F2 a, int l) { return pk(__shfl_sync(0xffffffffu, lo(a), l), __shfl_sync(0xffffffffu, hi(a), l)); }

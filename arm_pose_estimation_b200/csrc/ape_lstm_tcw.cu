@@ -38,6 +38,7 @@
 #include "ape_lstm_pack.h"
 #include "ape_lstm_tc_args.cuh"
 #include "ape_umma.cuh"
+#include "ape_f32x2.cuh"
 
 namespace ape {
 namespace tcw {
@@ -53,6 +54,9 @@ constexpr int THREADS = (EPI_WARPS + LOAD_WARPS + 4) * 32;   // 896 = 7 warpgrou
 // Which warps play which role.  The warp scheduler prefers the higher warp id among eligible warps, and the epilogue warps are
 // the ones the wave waits for: APE_TCW_EPI_HIGH = 1 gives them the highest ids (issuers + ring producer 0..3, loaders 4..11,
 // epilogue 12..27); 0 is the first layout (epilogue 0..15, loaders 16..23, issuers 24..25, producer 26).
+#ifndef APE_TCW_F32X2
+#define APE_TCW_F32X2 1
+#endif
 #ifndef APE_TCW_EPI_HIGH
 #define APE_TCW_EPI_HIGH 1
 #endif
@@ -300,6 +304,19 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                 }
 #endif
                 float hv[4], cn[4];
+#if APE_TCW_F32X2
+                // the cell update of two units per instruction (FFMA2 / FMUL2: the same IEEE operations as the scalar form, half the
+                // issue slots - the epilogue warps share their issue port with the XU queue they are waiting on)
+#pragma unroll
+                for (int u = 0; u < 4; u += 2) {
+                    const F2 half2 = splat(0.5f);
+                    const F2 gi = fma2(pk(tg[4 * u + 0], tg[4 * u + 4]), half2, half2), gf = fma2(pk(tg[4 * u + 1], tg[4 * u + 5]), half2, half2);
+                    const F2 c2 = fma2(gf, pk(cp[u], cp[u + 1]), gi * pk(tg[4 * u + 2], tg[4 * u + 6]));
+                    cn[u] = lo(c2); cn[u + 1] = hi(c2);
+                    const F2 h2 = fma2(pk(tg[4 * u + 3], tg[4 * u + 7]), half2, half2) * pk(tanh_approx(cn[u]), tanh_approx(cn[u + 1]));
+                    hv[u] = lo(h2); hv[u + 1] = hi(h2);
+                }
+#else
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float gi = fmaf(tg[4 * u + 0], 0.5f, 0.5f), gf = fmaf(tg[4 * u + 1], 0.5f, 0.5f);
@@ -307,6 +324,7 @@ lstm_pair_tcw_kernel(const __grid_constant__ TcLayerArgs a, const __grid_constan
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) hv[u] = fmaf(tg[4 * u + 3], 0.5f, 0.5f) * tanh_approx(cn[u]);
+#endif
                 if (t_cur + 1 < T) __stcg(cst_at(hp), make_float4(cn[0], cn[1], cn[2], cn[3]));
 
                 if (half == 0) {

@@ -592,8 +592,8 @@ def tc_split_leg(BatchedEstimator, N, syn, torch, kind, B, n, smooth, steps=40, 
 def ff_leg(N, torch, rows=1024, n=100, I=110, H=128, Lh=2, O=14, reps=20):
     """The MC-dropout feed-forward regressor (DropoutFF2D of the reference, nn_models.py:317-370; SURVEY.md §8 f.2 - no deployed model uses
     it): 1024 rows (streams) x 100 MC samples per launch of `ape_mc_ff`; algorithmic flops = hidden stack once per row + the output
-    layer per (row, sample), against the fp32 FMA peak measured in this run.  (One CTA per row; a variant that carried 8 rows per CTA
-    through the hidden stack measured 1.8x SLOWER - 128 CTAs of four active warps with one L2 load per FMA step - and was dropped.)"""
+    layer per (row, sample), against the fp32 FMA peak measured in this run.  (8 rows per CTA: W^T streamed through shared memory once per
+    CTA, thread = one (row, sample) pair in the output layer; the round-1 kernel - one CTA per row - took 0.252 ms for this launch.)"""
     import ctypes
     g = torch.Generator(device="cuda").manual_seed(5)
     floats = I * H + H + Lh * (H * H + H) + O * H + O
