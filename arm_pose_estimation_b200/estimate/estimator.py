@@ -6,8 +6,8 @@ them is different: the reference keeps the input window and the smoothing stack 
 CPU; here both histories are device rings indexed by the absolute frame number (a frame before 0 reads as frame 0, which is
 the reference's "repeat the first row / first prediction" start-up), owned by a one-stream ``BatchedEstimator``:
 
-* ``processing_loop`` / ``estimate_row``: one CUDA-graph launch per frame (H2D of the raw row, the three kernel stages, D2H
-  of the message) - the fused form of the loop body ``parse_row_to_xx -> add_xx_to_row_hist_and_make_prediction ->
+* ``processing_loop`` / ``estimate_row``: one CUDA-graph launch per frame (one H2D copy of frame counter + raw row, the three kernel stages,
+  the message written by stage 3 into mapped pinned memory) - the fused form of the loop body ``parse_row_to_xx -> add_xx_to_row_hist_and_make_prediction ->
   msg_from_pred`` (estimator.py:174-176);
 * the three calls one by one: each runs its own kernel stage (stage 1 with ``normalize=0``; ``ape_features_push`` + the
   MC-LSTM over the rings; stage 3 on the rows it is handed).
