@@ -587,6 +587,11 @@ static TcWsLayout tc_ws_layout(int H, int L, int T, long long E, int n_samples, 
     if (L >= 3) { const size_t s2 = ape::tcw::scratch_bytes(H, TC_MAX_SMS); if (s2 > w.scratch_region) w.scratch_region = s2; }
     const int n_u1 = L - 2 + (all_steps ? 1 : 0);
     w.total = 2 * w.scratch_region + 2 * w.u0 + (size_t)(n_u1 > 2 ? 2 : (n_u1 < 0 ? 0 : n_u1)) * w.u1 + 512;
+    // the small-batch cluster kernel (tc_flags == 4) keeps its exchange buffers where the layer kernels keep their units: one set per cluster
+    if (!all_steps && (H == 128 || H == 256) && E * n_samples <= 128LL * 64) {
+        const size_t need = 2 * w.scratch_region + ape::tcl::workspace_bytes(H, T, E * n_samples) + 512;
+        if (need > w.total) w.total = need;
+    }
     return w;
 }
 

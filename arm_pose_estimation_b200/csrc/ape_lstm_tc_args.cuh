@@ -125,10 +125,10 @@ int launch_pair(const tc::TcLayerArgs& a, const tc::TcLayerArgs& b, int sm_count
 }  // namespace tcw
 
 namespace tcl {
-// small-batch kernel (ape_lstm_tcl.cu): all layers of a call of <= 128 rows in one launch of one cluster of 8 CTAs (hidden units split
-// across the cluster, h_t exchanged once per step)
+// small-batch kernel (ape_lstm_tcl.cu): all layers of a call in one launch, one cluster of 8 CTAs per 128 rows (hidden units split
+// across the cluster, h_t exchanged once per step); up to 64 clusters
 bool supported(int H, int I, int L, int O, long long E, int n);
-size_t workspace_bytes(int H, int T);
+size_t workspace_bytes(int H, int T, long long rows);     // rows = E * n_samples of the largest call (one cluster per 128 rows)
 int run(const ape_lstm_args* g, const uint8_t* const* layer_w, const float* const* layer_bias, const uint8_t* wo16, void* workspace,
         cudaStream_t st);
 }  // namespace tcl

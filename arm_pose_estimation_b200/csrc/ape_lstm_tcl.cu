@@ -15,6 +15,10 @@
 // loader warps straight into TENSOR MEMORY one step ahead (tcgen05.st; the x-part MMAs take their A operand from TMEM), so shared
 // memory only holds the weights and the h tile.  Same operand rounding points, gate arithmetic (tanh form) and Philox keys as the
 // layer kernels; the fp16 weight blob is theirs (a CTA's slice = one or two of its 64-column tiles).
+// A call of more than 128 rows runs as SEVERAL clusters in the same launch, cluster c taking rows [128 c, 128 c + 128) of the layers >= 1 and
+// layer 0 of the estimates those rows belong to (rows are independent; an estimate that straddles two clusters has its layer 0 computed by
+// both): up to a few thousand rows - a few dozen real-time streams - this is faster than the layer kernels, which give every 256-row tile to
+// one CTA pair for T x L dependent passes over whole layers.
 #include "ape_common.cuh"
 #include "ape_lstm_pack.h"
 #include "ape_lstm_tc_args.cuh"
@@ -25,7 +29,7 @@ namespace tcl {
 
 using tc::tanh_approx;
 
-constexpr int NCTA = 8, ROWS = 128, MAX_L = 4;
+constexpr int NCTA = 8, ROWS = 128, MAX_L = 4, MAX_CLUSTERS = 64;
 // 12 loader warps: three per TMEM lane quarter, each taking every third k-group of its 32 rows (building x_t for a layer >= 1 is 32 L2
 // loads + 32 Philox draws per row at H = 256; with one warp per quarter it took 7.5 - 12 us, twice the rest of a step)
 // 8 epilogue warps: two per TMEM lane quarter, each taking every second k-group (8 units) of its 32 rows' cells
@@ -48,6 +52,7 @@ struct Args {
     float scale;                    // 1 / (1 - p) (1 with no dropout): applied to a layer's output sequence BEFORE the fp16 rounding
     uint4* hx;                      // [2][H/8][128] exchange buffer of h_t (operand layout), by step parity
     uint4* seq;                     // [2][T][H/8][128] a layer's output sequence (the next layer's input), by layer parity
+    size_t ws_stride;               // uint4s between the hx / seq buffers of consecutive clusters
     const uint8_t* Wo16;            // [2][H/8][NO][8]: fp16(W_o), remainder
     const float* bo;
     int O;
@@ -81,7 +86,14 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int T = a.T, L = a.L;
-    const int rows1 = a.E * a.n;                         // rows of the layers >= 1 (layer 0: E rows)
+    // this cluster's slab: rows [r0, r0 + rows1) of the layers >= 1 = (estimate, sample) pairs, and layer 0 of the estimates e_lo .. e_hi they belong to
+    const int cid = (int)(blockIdx.x / NCTA);
+    const int r0 = cid * ROWS;
+    const int rows1 = min(ROWS, a.E * a.n - r0);
+    const int e_lo = r0 / a.n, rows0 = (r0 + rows1 - 1) / a.n - e_lo + 1;
+    uint4* const hx = a.hx + (size_t)cid * a.ws_stride;  // [2][H/8][128] exchange buffer of h_t, by step parity
+    uint4* const seq = a.seq + (size_t)cid * a.ws_stride; // [2][T][H/8][128] a layer's output sequence, by layer parity
+    long long* const stamps = cid == 0 ? a.stamps : nullptr;
 
     if (warp == CTRL_WARP) {
         tmem_alloc<1>(tmem_slot, TMEM_COLS);
@@ -107,7 +119,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
     for (int l = 0; l < L; ++l) {
         const int kgx = a.kgx[l];
         const bool last_layer = l == L - 1;
-        const int rows = l == 0 ? a.E : rows1;
+        const int rows = l == 0 ? rows0 : rows1;
         // ---- this CTA's weight tiles of layer l -> shared memory (all MMAs of the previous layer have completed: see the barrier below) ----
         const uint32_t tile_bytes = (uint32_t)(kgx + KG) * KG_BYTES_B;
         if (warp == CTRL_WARP && lane == 0) {
@@ -136,11 +148,11 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
             for (int t = 0; t < T; ++t) {
                 mbar_wait_wd(&bars[BAR_ACC], ph_acc); ph_acc ^= 1;
                 fence_after_sync();
-                if (rank == 0 && tid == 0) stamp(a.stamps, l * T + t, 3);        // accumulators ready
+                if (rank == 0 && tid == 0) stamp(stamps, l * T + t, 3);        // accumulators ready
                 const bool exchange = t + 1 < T || (last_layer && a.preds);      // the last step's h only feeds the output layer
                 // this CTA's k-groups of the h_t tile / of the layer's output sequence: [k-group rank NU/8 + b8][row]
-                uint4* hx_dst = a.hx + (size_t)(t & 1) * KG * ROWS + (size_t)(rank * (NU / 8)) * ROWS + row;
-                uint4* seq_dst = a.seq + ((size_t)(l & 1) * T + t) * KG * ROWS + (size_t)(rank * (NU / 8)) * ROWS + row;
+                uint4* hx_dst = hx + (size_t)(t & 1) * KG * ROWS + (size_t)(rank * (NU / 8)) * ROWS + row;
+                uint4* seq_dst = seq + ((size_t)(l & 1) * T + t) * KG * ROWS + (size_t)(rank * (NU / 8)) * ROWS + row;
 #pragma unroll
                 for (int i8 = 0; i8 < NB8; ++i8) {         // 8 units = 32 accumulator columns = one k-group at a time
                     const int b8 = EPI_PARTS * i8 + epart;
@@ -167,7 +179,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
                         seq_dst[(size_t)b8 * ROWS] = make_uint4(pack_half2(hv[0] * a.scale, hv[1] * a.scale), pack_half2(hv[2] * a.scale, hv[3] * a.scale),
                                                                 pack_half2(hv[4] * a.scale, hv[5] * a.scale), pack_half2(hv[6] * a.scale, hv[7] * a.scale));
                 }
-                if (rank == 0 && tid == 0) stamp(a.stamps, l * T + t, 4);        // cell update done, slice written
+                if (rank == 0 && tid == 0) stamp(stamps, l * T + t, 4);        // cell update done, slice written
                 fence_before_sync();
                 cluster_sync();                            // every slice of h_t (and of the layer's sequence) is written, every MMA of step t done
                                                            // (release / acquire at cluster scope covers the global writes of the sequence)
@@ -180,7 +192,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
                 else { tmem_ld_x32(tmem + t_lane + OUT_COL, o); tmem_ld_x32(tmem + t_lane + OUT_COL + 32, o + 32); }
                 tmem_ld_wait();
                 if (row < rows) {
-                    const int e = row / a.n, smp = row - e * a.n;
+                    const int e = (r0 + row) / a.n, smp = r0 + row - e * a.n;
                     const int bb = e / a.nF, fb = stream_frame0(a.stream_frames, a.frame0, bb), f = fb + e % a.nF;
                     if (fb >= 0) {
                         float* dst = a.preds + ((((size_t)bb * a.pred_ring + f % a.pred_ring) * a.n) + smp) * a.O;
@@ -196,7 +208,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
             const int lw = warp & 3, part = (warp - EPI_WARPS) >> 2, row = 32 * lw + lane;   // (warp % 4 == lw: its TMEM lane quarter)
             const uint32_t t_lane = (uint32_t)(32 * lw) << 16;
             const bool valid = row < rows;
-            const int e = valid ? (l == 0 ? row : row / a.n) : 0, smp = (valid && l > 0) ? row - e * a.n : 0;
+            const int e = valid ? (l == 0 ? e_lo + row : (r0 + row) / a.n) : 0, smp = (valid && l > 0) ? r0 + row - e * a.n : 0;
             const int bidx = e / a.nF, f = stream_frame0(a.stream_frames, a.frame0, bidx) + e % a.nF;
             const uint32_t stream = a.stream_id0 + (uint32_t)bidx;
             // x_t goes into X buffer t & 1, which the x-part MMAs of step t-2 read: those are complete once the cluster barrier that ends
@@ -206,7 +218,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
                 if (l == 0) {
                     const float* src = nullptr;
                     if (valid) {
-                        if (a.dense) src = a.in + ((size_t)row * T + t) * a.I;
+                        if (a.dense) src = a.in + ((size_t)e * T + t) * a.I;
                         else {                             // sliding window, clamped at frame 0 (estimator.py:96-97)
                             int fw = f - T + 1 + t;
                             fw = fw < 0 ? 0 : fw;
@@ -221,7 +233,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
                     }
                 } else {
                     // the previous layer's h_t (fp16 units scaled by 1 / (1 - p)) of this row's estimate, dropout mask of gap l - 1 ANDed in
-                    const uint4* src = a.seq + ((size_t)((l - 1) & 1) * T + t) * KG * ROWS + (l == 1 ? e : row);
+                    const uint4* src = seq + ((size_t)((l - 1) & 1) * T + t) * KG * ROWS + (l == 1 ? e - e_lo : row);
                     // all KG loads of the step go out before anything else: they come from L2 (written by other SMs), and two at a time
                     // had been the longest chain of a step (16 L2 round trips: 7.9 us per step for the whole kernel)
                     constexpr int NJ = (KG + LOAD_PARTS - 1) / LOAD_PARTS;       // this warp's k-groups: part, part + 3, ...
@@ -276,7 +288,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
             for (int t = 0; t < T; ++t) {
                 mbar_wait_wd(&bars[BAR_X + (t & 1)], ph_x[t & 1]); ph_x[t & 1] ^= 1;
                 fence_after_sync();
-                if (rank == 0 && lane == 0) stamp(a.stamps, l * T + t, 0);       // x_t ready
+                if (rank == 0 && lane == 0) stamp(stamps, l * T + t, 0);       // x_t ready
                 if (elect_one()) {
                     const uint32_t xa = tmem + X_COL + (uint32_t)(t & 1) * (H / 2);
 #pragma unroll
@@ -296,7 +308,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
                 if (t > 0) {
                     mbar_wait_wd(&bars[BAR_H], ph_h); ph_h ^= 1;             // h_{t-1} of all units is in sH
                     fence_after_sync();
-                    if (rank == 0 && lane == 0) stamp(a.stamps, l * T + t, 1);   // h_{t-1} landed
+                    if (rank == 0 && lane == 0) stamp(stamps, l * T + t, 1);   // h_{t-1} landed
                     if (elect_one()) {
 #pragma unroll
                         for (int b = 0; b < NB; ++b) {
@@ -310,17 +322,17 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
                 }
                 if (elect_one()) commit(&bars[BAR_ACC]);
                 __syncwarp();
-                if (rank == 0 && lane == 0) stamp(a.stamps, l * T + t, 2);       // MMAs issued + committed
+                if (rank == 0 && lane == 0) stamp(stamps, l * T + t, 2);       // MMAs issued + committed
                 fence_before_sync();
                 cluster_sync();                            // end of step t: every CTA's slice of h_t is in the exchange buffer
-                if (rank == 0 && lane == 0) stamp(a.stamps, l * T + t, 5);       // barrier passed
+                if (rank == 0 && lane == 0) stamp(stamps, l * T + t, 5);       // barrier passed
                 // pull the whole h_t tile (after the last step only CTA 0 needs h_T - for the output product - and a copy nobody waits for
                 // must not be in flight at exit)
                 const bool pull = t + 1 < T || (last_layer && a.preds && rank == 0);
                 if (pull && lane == 0) {
                     asm volatile("fence.proxy.async;" ::: "memory");        // generic-proxy writes of the other SMs -> this bulk copy
                     mbar_arrive_expect_tx(&bars[BAR_H], H_BYTES);
-                    bulk_g2s(sH, a.hx + (size_t)(t & 1) * KG * ROWS, H_BYTES, &bars[BAR_H]);
+                    bulk_g2s(sH, hx + (size_t)(t & 1) * KG * ROWS, H_BYTES, &bars[BAR_H]);
                 }
                 __syncwarp();
             }
@@ -354,17 +366,21 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
 }
 
 bool supported(int H, int I, int L, int O, long long E, int n) {
-    return (H == 128 || H == 256) && L >= 2 && L <= MAX_L && E >= 1 && E <= ROWS && E * n <= ROWS &&
+    return (H == 128 || H == 256) && L >= 2 && L <= MAX_L && E >= 1 && n >= 1 && E * n <= (long long)ROWS * MAX_CLUSTERS &&
            ape_pack_kin_pad(0, I, H) <= H && O <= (H > 128 ? 32 : 16);
 }
 
-size_t workspace_bytes(int H, int T) { return (size_t)(2 + 2 * T) * (H / 8) * ROWS * 16 + 256; }
+static size_t cluster_ws_bytes(int H, int T) { return (size_t)(2 + 2 * T) * (H / 8) * ROWS * 16; }      // hx + seq of one cluster
+size_t workspace_bytes(int H, int T, long long rows) {
+    const long long clusters = rows <= 0 ? 1 : (rows + ROWS - 1) / ROWS;
+    return cluster_ws_bytes(H, T) * (size_t)clusters + 256;
+}
 
-template <int H> static int launch_t(const Args& a, cudaStream_t st) {
+template <int H> static int launch_t(const Args& a, int clusters, cudaStream_t st) {
     constexpr int KG = H / 8, NB = H / NCTA / 16;
     const size_t smem = (size_t)NB * 2 * KG * KG_BYTES_B + (size_t)KG * ROWS * 16 + (size_t)4 * (H / NCTA) * 4 + 64;
     APE_CUDA_TRY(cudaFuncSetAttribute(lstm_small_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lstm_small_kernel<H><<<NCTA, THREADS, smem, st>>>(a);
+    lstm_small_kernel<H><<<NCTA * clusters, THREADS, smem, st>>>(a);
     return check_launch();
 }
 
@@ -391,12 +407,14 @@ int run(const ape_lstm_args* g, const uint8_t* const* layer_w, const float* cons
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     a.hx = (uint4*)ws;
     a.seq = (uint4*)(ws + (size_t)2 * (g->H / 8) * ROWS * 16);
+    a.ws_stride = cluster_ws_bytes(g->H, g->T) / 16;
+    const int clusters = (int)((E * g->n_samples + ROWS - 1) / ROWS);
     a.Wo16 = wo16;
     a.bo = g->weights + ape_pack_out_offset(g->I, g->H, g->L) + (size_t)g->O * g->H;
     a.O = g->O;
     a.preds = g->preds; a.pred_ring = g->pred_ring;
     a.stamps = (g->trace && g->trace_layer == -2) ? (long long*)g->trace : nullptr;
-    return g->H == 256 ? launch_t<256>(a, st) : launch_t<128>(a, st);
+    return g->H == 256 ? launch_t<256>(a, clusters, st) : launch_t<128>(a, clusters, st);
 }
 
 }  // namespace tcl

@@ -113,6 +113,8 @@ class _GraphCall:
 
 
 class BatchedEstimator:
+    # largest call (streams x frames x MC samples) that runs on the cluster kernel (one 8-CTA cluster per 128 rows, csrc/ape_lstm_tcl.cu)
+    SMALL_BATCH_ROWS = int(os.environ.get("APE_SMALL_BATCH_ROWS", "2048"))
     N_SLOTS = int(os.environ.get("APE_N_SLOTS", "8"))      # staging / result buffer sets: up to N_SLOTS - 1 submitted calls may be outstanding while the next is staged
                      # (measured end to end, uarm 1024 x 100: 3 outstanding 0.413 ms/step, 5 outstanding 0.392, 7 outstanding 0.391)
 
@@ -223,10 +225,12 @@ class BatchedEstimator:
                         self.workspace = torch.empty(ws_x, dtype=torch.uint8, device=dev)
             # A call of <= 128 rows (one stream x 100 MC samples: the real-time case) can run ALL layers in one launch of one 8-CTA cluster
             # with the hidden units split across it (csrc/ape_lstm_tcl.cu) instead of one CTA pair walking every gate column of every
-            # layer.  Same operand rounding, accumulation order and Philox keys as the layer kernels: results are bit-identical
+            # layer; a larger call takes one cluster per 128 rows in the same launch.  Up to 16 clusters (what a B200 holds at once: two per
+            # GPC) the call costs what one cluster costs - measured per call, pocket model x 100 MC samples: 1 .. 16 streams 0.10 ms against
+            # 0.19 ms on the layer kernels, 32 streams 0.16 against 0.19, 64 streams 0.27 against 0.19 (tools/tcl_crossover.py).  Same operand rounding, accumulation order and Philox keys as the layer kernels: results are bit-identical
             # (tests/test_gpu_tcl.py), so it is simply what such an estimator runs (small_batch_kernel=False: the layer kernels).
             self.small_batch = (bool(small_batch_kernel) and self.lstm_variant == "tc" and not self.tc_split and self.tc_flags == 0
-                                and self.L <= 4 and self.H in (128, 256) and B * nF * self.n <= 128)
+                                and self.L <= 4 and self.H in (128, 256) and B * nF * self.n <= self.SMALL_BATCH_ROWS)
             if self.small_batch:
                 self.tc_flags = 4
             # cross-call software pipeline (tensor-core path), two levels:

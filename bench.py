@@ -798,6 +798,24 @@ def realtime_latency(BatchedEstimator, N, syn, frames=300):
     for _ in range(3):
         ref.step_device(dev, layer_ms=lm)
     out["layer_kernels_lstm_device_ms"] = float(lm.sum())
+    # the multi-stream real-time front-end's tick: 16 streams x 100 MC samples per graph launch - one cluster per 128 rows
+    # of the call in the same launch of the small-batch kernel, against the layer kernels (one CTA pair per 256-row tile)
+    ms = {}
+    for key, kw in (("p50_ms", {}), ("layer_kernels_p50_ms", {"small_batch_kernel": False})):
+        eng = BatchedEstimator(kind=kind, layout=spec["layout"], state=state, seq_len=spec["T"], y_targets=spec["y_targets"], stats=spec["stats"],
+                               n_streams=16, mc_samples=100, smooth=1, dropout=spec["p"], frames_per_call=1, mask_mode=N.MASK_PHILOX,
+                               philox_seed=7, **kw)
+        rows16 = syn.synth_rows(kind, 16, 220, config_id=2)
+        lat = []
+        for f in range(220):
+            t0 = time.perf_counter()
+            eng.step_graph(rows16[:, f:f + 1])
+            lat.append(time.perf_counter() - t0)
+        lat = np.asarray(lat[20:]) * 1e3
+        ms[key] = float(np.percentile(lat, 50))
+        if not kw:
+            ms["p99_ms"], ms["clusters"] = float(np.percentile(lat, 99)), (16 * 100 + 127) // 128 if eng.small_batch else 0
+    out["multi_stream_16x100"] = ms
     return out
 
 

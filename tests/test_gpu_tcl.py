@@ -1,5 +1,6 @@
-"""GPU (-m gpu): the small-batch cluster kernel (csrc/ape_lstm_tcl.cu: all layers of a call of <= 128 rows in one launch of one
-8-CTA cluster, hidden units split across the cluster) - what a single-stream estimator runs per frame (BASELINE configs[1]).
+"""GPU (-m gpu): the small-batch cluster kernel (csrc/ape_lstm_tcl.cu: all layers of a call in one launch, one 8-CTA cluster per 128
+rows, hidden units split across the cluster) - what a single-stream estimator runs per frame (BASELINE configs[1]) and what a few
+dozen real-time streams run per tick.
 It keeps the layer kernels' operand rounding points, accumulation order and Philox keys, so it must be BIT-identical to them;
 and like them it is checked against the reference's own messages and the oracle."""
 import numpy as np
@@ -18,7 +19,10 @@ KINDS = [syn.KIND_WATCH_ONLY, syn.KIND_POCKET, syn.KIND_UARM]
 
 @pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("B,n,nF,mode", [(1, 100, 1, N.MASK_PHILOX), (1, 1, 1, N.MASK_PHILOX), (3, 40, 1, N.MASK_PHILOX), (2, 16, 4, N.MASK_INJECTED),
-                                         (1, 128, 1, N.MASK_INJECTED)])
+                                         (1, 128, 1, N.MASK_INJECTED),
+                                         # several clusters in one launch (one per 128 rows): estimates that straddle two clusters, more
+                                         # estimates than a cluster has rows, several frames per call, the largest call the estimator gives it
+                                         (3, 100, 1, N.MASK_PHILOX), (130, 1, 1, N.MASK_PHILOX), (20, 7, 2, N.MASK_INJECTED), (16, 128, 1, N.MASK_PHILOX)])
 def test_small_batch_kernel_is_bit_identical_to_the_layer_kernels(kind, B, n, nF, mode):
     rows = syn.synth_rows(kind, B, 3 * nF, config_id=6)
     kw = dict(frames_per_call=nF, mask_mode=mode, philox_seed=11, smooth=2)
