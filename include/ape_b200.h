@@ -143,8 +143,9 @@ typedef struct ape_lstm_args {
        two-layer wavefront launch, csrc/ape_lstm_tcw.cu, when the batch fills the GPU), 1 = one launch per layer always,
        2 = wavefront pairs always, 3 = the SPLIT-PRECISION variant (every operand an fp16 pair hi + lo, three tensor-core passes per
        product, ex2 / rcp cell update: fp32-grade results at ~1/2 of the single-pass throughput; needs weights_tcx),
-       4 = the SMALL-BATCH kernel (csrc/ape_lstm_tcl.cu: B * nF * n_samples <= 128 rows, L <= 4: all layers in one launch of one
-       8-CTA cluster with the hidden units split across it - the single-stream real-time case; same arithmetic as 0..2) */
+       4 = the SMALL-BATCH kernel (csrc/ape_lstm_tcl.cu: B * nF * n_samples <= 8192 rows, L <= 4: all layers in one launch, one
+       8-CTA cluster per 128 rows with the hidden units split across it - the real-time case of one to a few dozen streams; same
+       arithmetic as 0..2) */
     int tc_flags;
     /* fp32 path: optional initial state (h_0, c_0) of torch.nn.LSTM(x, hs) (nn_models.py:180-189): [L][E][H] float32 each, both
        or neither; needs n_samples == 1 (a caller with per-sample states passes the samples as estimates) */
