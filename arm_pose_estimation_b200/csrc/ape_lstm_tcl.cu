@@ -23,6 +23,7 @@
 #include "ape_lstm_pack.h"
 #include "ape_lstm_tc_args.cuh"
 #include "ape_umma.cuh"
+#include "ape_f32x2.cuh"
 
 namespace ape {
 namespace tcl {
@@ -161,16 +162,22 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1) lstm_
                     tmem_ld_wait();
                     float hv[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float4 bs = sBias4[8 * b8 + u];                      // 0.5 b (i, f, o), b (g)
-                        const float ti = tanh_approx(fmaf(__uint_as_float(r[4 * u + 0]), 0.5f, bs.x));
-                        const float tf = tanh_approx(fmaf(__uint_as_float(r[4 * u + 1]), 0.5f, bs.y));
-                        const float tg = tanh_approx(__uint_as_float(r[4 * u + 2]) + bs.z);
-                        const float to = tanh_approx(fmaf(__uint_as_float(r[4 * u + 3]), 0.5f, bs.w));
-                        const float gi = fmaf(ti, 0.5f, 0.5f), gf = fmaf(tf, 0.5f, 0.5f);
-                        const float c = fmaf(gf, cst[8 * i8 + u], gi * tg);
-                        cst[8 * i8 + u] = c;
-                        hv[u] = fmaf(to, 0.5f, 0.5f) * tanh_approx(c);
+                    for (int u = 0; u < 8; u += 2) {                               // two units per instruction (packed fp32 pairs, ape_f32x2.cuh: the scalar operations bit for bit)
+                        float tg[8];
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) {
+                            const float4 bs = sBias4[8 * b8 + u + v];              // 0.5 b (i, f, o), b (g)
+                            const F2 aif = fma2(pk(__uint_as_float(r[4 * (u + v) + 0]), __uint_as_float(r[4 * (u + v) + 1])), splat(0.5f), pk(bs.x, bs.y));
+                            const F2 ago = fma2(pk(__uint_as_float(r[4 * (u + v) + 2]), __uint_as_float(r[4 * (u + v) + 3])), pk(1.0f, 0.5f), pk(bs.z, bs.w));
+                            tg[4 * v + 0] = tanh_approx(lo(aif)); tg[4 * v + 1] = tanh_approx(hi(aif));
+                            tg[4 * v + 2] = tanh_approx(lo(ago)); tg[4 * v + 3] = tanh_approx(hi(ago));
+                        }
+                        const F2 h2c = splat(0.5f);
+                        const F2 gi = fma2(pk(tg[0], tg[4]), h2c, h2c), gf = fma2(pk(tg[1], tg[5]), h2c, h2c);
+                        const F2 c2 = fma2(gf, pk(cst[8 * i8 + u], cst[8 * i8 + u + 1]), gi * pk(tg[2], tg[6]));
+                        cst[8 * i8 + u] = lo(c2); cst[8 * i8 + u + 1] = hi(c2);
+                        const F2 h2 = fma2(pk(tg[3], tg[7]), h2c, h2c) * pk(tanh_approx(lo(c2)), tanh_approx(hi(c2)));
+                        hv[u] = lo(h2); hv[u + 1] = hi(h2);
                     }
                     // h_t as fp16 units: as is for the recurrence, scaled by the consumer's 1 / (1 - p) (before the rounding) for the next layer
                     if (exchange)

@@ -31,6 +31,10 @@
 #include "ape_lstm_pack.h"
 #include "ape_lstm_tc_args.cuh"
 #include "ape_umma.cuh"
+#include "ape_f32x2.cuh"
+#ifndef APE_TCS_F32X2
+#define APE_TCS_F32X2 1
+#endif
 
 namespace ape {
 namespace tcs {
@@ -335,11 +339,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                                 continue;
                             }
 #endif
+#if APE_TCS_F32X2 && APE_EXP != 7
+                            // tanh arguments in packed fp32 pairs (ape_f32x2.cuh): (i, f) and (g, o) sit in adjacent accumulator registers and
+                            // adjacent bias words, r * (0.5, 0.5) + b and r * (1, 0.5) + b are the scalar operations bit for bit
+                            const F2 aif = fma2(pk(__uint_as_float(r[4 * u + 0]), __uint_as_float(r[4 * u + 1])), splat(0.5f), pk(bs.x, bs.y));
+                            const F2 ago = fma2(pk(__uint_as_float(r[4 * u + 2]), __uint_as_float(r[4 * u + 3])), pk(1.0f, 0.5f), pk(bs.z, bs.w));
+                            tg[4 * u + 0] = tanh_approx(lo(aif)); tg[4 * u + 1] = tanh_approx(hi(aif));
+                            tg[4 * u + 2] = tanh_approx(lo(ago)); tg[4 * u + 3] = tanh_approx(hi(ago));
+#else
                             tg[4 * u + 0] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 0]), 0.5f, bs.x));
                             tg[4 * u + 1] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 1]), 0.5f, bs.y));
                             tg[4 * u + 2] = tanh_approx(__uint_as_float(r[4 * u + 2]) + bs.z);
                             tg[4 * u + 3] = tanh_approx(fmaf(__uint_as_float(r[4 * u + 3]), 0.5f, bs.w));
+#endif
                         }
+#if APE_TCS_F32X2 && APE_EXP != 7
+#pragma unroll
+                        for (int u = 0; u < 4; u += 2) {               // the cell update of two units per instruction (as in ape_lstm_tcw.cu)
+                            const F2 h2c = splat(0.5f);
+                            const F2 gi = fma2(pk(tg[4 * u + 0], tg[4 * u + 4]), h2c, h2c), gf = fma2(pk(tg[4 * u + 1], tg[4 * u + 5]), h2c, h2c);
+                            const F2 c2 = fma2(gf, pk(cp[u], cp[u + 1]), gi * pk(tg[4 * u + 2], tg[4 * u + 6]));
+                            cn[u] = lo(c2); cn[u + 1] = hi(c2);
+                            const F2 h2 = fma2(pk(tg[4 * u + 3], tg[4 * u + 7]), h2c, h2c) * pk(tanh_approx(cn[u]), tanh_approx(cn[u + 1]));
+                            hv[u] = lo(h2); hv[u + 1] = hi(h2);
+                        }
+#else
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const float gi = fmaf(tg[4 * u + 0], 0.5f, 0.5f), gf = fmaf(tg[4 * u + 1], 0.5f, 0.5f);
@@ -347,6 +371,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) hv[u] = fmaf(tg[4 * u + 3], 0.5f, 0.5f) * ((APE_EXP == 7 && (s & 1)) ? cn[u] * 0.1f : tanh_approx(cn[u]));
+#endif
 #else
                         float ev[16], num[4], den[4];
 #pragma unroll
