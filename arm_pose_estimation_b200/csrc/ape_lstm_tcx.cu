@@ -169,9 +169,12 @@ lstm_layer_tcx_kernel(const __grid_constant__ TcLayerArgs a) {
             for (int hp = 0; hp < 2 * NCHL; ++hp) {
                 const int cl = hp >> 1, half = hp & 1, slot = cl & 1;
                 tmem_ld_wait();
-                float pa[16];
+                float pa[16];                                  // ex2 arguments (bias is in the accumulator); two columns per multiply
 #pragma unroll
-                for (int i = 0; i < 16; ++i) pa[i] = __uint_as_float(r[i]) * NEG2LOG2E;   // ex2 arguments (bias is in the accumulator)
+                for (int i = 0; i < 16; i += 2) {
+                    const F2 v = pk(__uint_as_float(r[i]), __uint_as_float(r[i + 1])) * splat(NEG2LOG2E);
+                    pa[i] = lo(v); pa[i + 1] = hi(v);
+                }
                 if (half == 1) {                               // chunk drained: its issuer may refill the slot
                     fence_before_sync();
                     __syncwarp();
@@ -182,9 +185,12 @@ lstm_layer_tcx_kernel(const __grid_constant__ TcLayerArgs a) {
                 if (half == 0) tmem_ld_x16(acc0 + (uint32_t)(slot * 128 + 16), r);
                 float hv[4], cn[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    cn[u] = cp[u];
-                    tc::lstm_cell(pa[4 * u + 0], pa[4 * u + 1], pa[4 * u + 2], pa[4 * u + 3], cn[u], hv[u]);
+                for (int u = 0; u < 4; u += 2) {               // two cells per instruction stream (packed fp32 pairs)
+                    F2 c2 = pk(cp[u], cp[u + 1]), h2;
+                    tc::lstm_cell2(pk(pa[4 * u + 0], pa[4 * u + 4]), pk(pa[4 * u + 1], pa[4 * u + 5]), pk(pa[4 * u + 2], pa[4 * u + 6]),
+                                   pk(pa[4 * u + 3], pa[4 * u + 7]), c2, h2);
+                    cn[u] = lo(c2); cn[u + 1] = hi(c2);
+                    hv[u] = lo(h2); hv[u + 1] = hi(h2);
                 }
                 if (t + 1 < T) __stcg(cst_at(hp), make_float4(cn[0], cn[1], cn[2], cn[3]));
                 if (half == 0) {
