@@ -7,6 +7,10 @@
 // counter-based Philox) is applied when a layer READS its input, so layer 0 is evaluated once per estimate
 // and only layers >= 1 are evaluated per MC sample.  Sequences between layers use the
 // tile-local K-major layout [tile][T][H][R] so both sides move float4s with unit stride.
+#include "ape_f32x2.cuh"
+#ifndef APE_FMA_F32X2
+#define APE_FMA_F32X2 1
+#endif
 #include "ape_common.cuh"
 #include "ape_lstm_pack.h"
 #include "ape_lstm_plan.cuh"
@@ -224,6 +228,20 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerAr
                     ld_vec<RT>(As + kk * R, av);
                     const float4 b0 = *reinterpret_cast<const float4*>(Bs + kk * CHUNK_COLS);
                     const float4 b1 = *reinterpret_cast<const float4*>(Bs + kk * CHUNK_COLS + 64);
+#if APE_FMA_F32X2
+                    // two gate columns per FFMA2 (packed fp32 pairs, ape_f32x2.cuh; the row value is a scalar-broadcast operand): the same
+                    // fused multiply-adds in the same order, half the issue slots of the contraction
+                    const F2 w01 = pk(b0.x, b0.y), w23 = pk(b0.z, b0.w), w45 = pk(b1.x, b1.y), w67 = pk(b1.z, b1.w);
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const F2 x = splat(av[r]);
+                        F2 v;
+                        v = fma2(w01, x, pk(acc[r][0], acc[r][1])); acc[r][0] = lo(v); acc[r][1] = hi(v);
+                        v = fma2(w23, x, pk(acc[r][2], acc[r][3])); acc[r][2] = lo(v); acc[r][3] = hi(v);
+                        v = fma2(w45, x, pk(acc[r][4], acc[r][5])); acc[r][4] = lo(v); acc[r][5] = hi(v);
+                        v = fma2(w67, x, pk(acc[r][6], acc[r][7])); acc[r][6] = lo(v); acc[r][7] = hi(v);
+                    }
+#else
 #pragma unroll
                     for (int r = 0; r < RT; ++r) {
                         acc[r][0] = fmaf(av[r], b0.x, acc[r][0]); acc[r][1] = fmaf(av[r], b0.y, acc[r][1]);
@@ -231,6 +249,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_fma_kernel(LayerAr
                         acc[r][4] = fmaf(av[r], b1.x, acc[r][4]); acc[r][5] = fmaf(av[r], b1.y, acc[r][5]);
                         acc[r][6] = fmaf(av[r], b1.z, acc[r][6]); acc[r][7] = fmaf(av[r], b1.w, acc[r][7]);
                     }
+#endif
                 }
             }
             // ---- cell update for this thread's RT rows x 2 units (gate order i, f, g, o) ------------------
