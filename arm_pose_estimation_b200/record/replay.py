@@ -146,9 +146,10 @@ def relabel_recordings(recordings, make_estimator, frames_per_call=16, keep_samp
             collect(*outstanding.pop(0))
     for item in outstanding:
         collect(*item)
+    msg64, std64 = msg.astype(np.float64), std.astype(np.float64)      # one conversion for all recordings; the per-recording results are views
     res = []
     for i in range(R):
-        d = dict(msg=msg[i, : lengths[i]].astype(np.float64), std=std[i, : lengths[i]].astype(np.float64))
+        d = dict(msg=msg64[i, : lengths[i]], std=std64[i, : lengths[i]])
         if keep_samples:
             d["samples"] = samples[i, : lengths[i]]
         res.append(d)
