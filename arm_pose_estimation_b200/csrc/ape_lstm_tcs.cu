@@ -49,10 +49,23 @@ using tc::tanh_approx;
 
 constexpr int EPI_WARPS = 16, LOAD_WARPS = 4;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS;   // leader CTA: MMA issuers (MMA_WARP + k issues the chunks of accumulator slot k);
-constexpr int N_ISSUERS = 2;                       //   peer CTA: the first of them forwards "piece landed" to the leader
-constexpr int TMA_WARP = MMA_WARP + N_ISSUERS;     // one lane per CTA fills the weight ring
+constexpr int N_ISSUERS = 2;                       // leader CTA: MMA issuers (MMA_WARP + k issues the chunks of accumulator slot k);
+                                                   //   peer CTA: the first of them forwards "piece landed" to the leader
+// Which warps play which role: epilogue 0..15, loaders 16..19, issuers 20..21, producer 22.  APE_TCS_EPI_HIGH = 1 is the layout that
+// gained 1.3 % in ape_lstm_tcw.cu (epilogue warps on the highest ids, which the scheduler prefers among eligible warps: issuers 0..1,
+// producer 2, one idle warp, loaders 4..7, epilogue 8..23); here it measured 3.7 % SLOWER (layer-1 launch 0.652 against 0.628 ms: the CTA
+// grows to 768 threads = 80 registers instead of 88, and this kernel waits for its issuers rather than for its epilogue) and stays off.
+#ifndef APE_TCS_EPI_HIGH
+#define APE_TCS_EPI_HIGH 0
+#endif
+#if APE_TCS_EPI_HIGH
+constexpr int MMA_WARP = 0, TMA_WARP = MMA_WARP + N_ISSUERS, LOAD_WARP0 = 4, EPI_WARP0 = LOAD_WARP0 + LOAD_WARPS;
+constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // 768: 80 registers per thread
+#else
+constexpr int EPI_WARP0 = 0, LOAD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + LOAD_WARPS, TMA_WARP = MMA_WARP + N_ISSUERS;
 constexpr int THREADS = (TMA_WARP + 1) * 32;       // 736: 88 registers per thread
+#endif
+static_assert(EPI_WARP0 % 4 == 0 && LOAD_WARP0 % 4 == 0, "TMEM lane quarter = warp % 4; loader rows = thread index within the role");
 constexpr int ROWS = 128;                          // rows per CTA = TMEM lanes
 constexpr int NSLOT = 2;                           // accumulator slots of 128 TMEM columns
 constexpr int SLICE_KG = 4;                        // k-groups (of 8 K-values) per published K-slice of h_t (one chunk's 32 units)
@@ -233,10 +246,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
     const uint32_t tmem = *tmem_slot;
     tc::timeline_stamp(a.timeline, 1);
 
-    if (warp < EPI_WARPS) {
+    if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
         // =================================== epilogue warps ===========================================================
         // warp (q, s): rows 32q..32q+31 (its TMEM lane quarter) x the 8 hidden units 8s..8s+7 of EVERY 32-unit chunk.
-        const int q = warp & 3, s = warp >> 2;
+        const int q = warp & 3, s = (warp - EPI_WARP0) >> 2;
         const int row_l = 32 * q + lane;                       // local row == TMEM lane
         const uint32_t t_lane = (uint32_t)(32 * q) << 16;
         const bool warp_live = 32 * q < a.rpc;                 // a quarter without rows only keeps the barrier protocol going
@@ -464,11 +477,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 }
             }
         }
-    } else if (warp < MMA_WARP) {
+    } else if (warp >= LOAD_WARP0 && warp < LOAD_WARP0 + LOAD_WARPS) {
         // =================================== operand-loader warps: x_t -> sAx ===========================================
         constexpr int TPR = LOAD_WARPS * 32 / ROWS;            // loader threads per row, each an equal share of the x k-groups
-        const int row_l = (tid - EPI_THREADS) & (ROWS - 1);
-        const int part = (tid - EPI_THREADS) / ROWS;
+        const int row_l = (tid - LOAD_WARP0 * 32) & (ROWS - 1);
+        const int part = (tid - LOAD_WARP0 * 32) / ROWS;
         uint32_t gl = 0;                                       // steps loaded so far: step gl goes to x buffer gl & 1
         for (int tile = cluster_id; tile < a.n_pair_tiles; tile += n_clusters) {
             const int row = (tile * 2 + (int)rank) * a.rpc + row_l;
@@ -479,7 +492,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 uint8_t* sX = sAx + (gl & 1) * C::A_BYTES;
                 // the tile written two steps ago has been consumed (the loader may run up to two steps ahead of the MMAs)
                 auto wait_buffer = [&]() { if (gl >= 2) mbar_wait_wd(&bars[C::BAR_X_DONE + (gl & 1)], ((gl >> 1) & 1) ^ 1); };
-                TCS_TR(const bool trl = a.trace && blockIdx.x == 0 && tile == cluster_id && t == TRACE_T && tid == EPI_THREADS;)
+                TCS_TR(const bool trl = a.trace && blockIdx.x == 0 && tile == cluster_id && t == TRACE_T && tid == LOAD_WARP0 * 32;)
                 if (a.in_mode == tc::IN_UNITS || a.in_mode == tc::IN_SHARED_UNITS) {
                     // The first batch of 8 k-groups is fetched and masked before anything waits; only the shared-memory
                     // stores (and the remaining batches, which would not fit the register file) sit behind "the previous
@@ -552,7 +565,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
                 TCS_TR(if (trl) a.trace[582] = clock64();)
             }
         }
-    } else if (warp < TMA_WARP) {
+    } else if (warp >= MMA_WARP && warp < MMA_WARP + N_ISSUERS) {
         if (rank == 0) {
             // =============================== MMA issuers (leader CTA; the whole warp runs, one elected lane issues) =====
             // Issuer k owns the chunks of accumulator slot k: a single issuing thread spends ~650 cycles of waits and table
@@ -716,7 +729,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_lay
             }
             if (out_pending) forward();
         }
-    } else if (lane == 0) {
+    } else if (warp == TMA_WARP && lane == 0) {
         // =================================== weight-ring producer (one lane per CTA) =====================================
         const uint8_t* Wc = a.W + (size_t)rank * w_bytes;      // this CTA's half of the layer's weight tiles
         uint32_t wslot = 0, wphase = 0, gpiece = 0;
