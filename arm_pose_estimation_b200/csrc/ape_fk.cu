@@ -9,14 +9,16 @@
 
 namespace ape {
 
-// Resident CTAs per SM -> registers per thread.  With the next row prefetched the kernel wants 80 registers (O = 12) / 96 (O = 14, 20):
-// at 64 it spills 45 values per pass.  Measured on B200, 32 768 estimates x 100 rows: O = 12: 8 / 6 / 5 CTAs = 0.080 / 0.068 / 0.070 ms,
-// O = 14: 0.109 / 0.089 / 0.076 ms.
-#ifndef APE_FK_MIN_BLOCKS
-#define APE_FK_MIN_BLOCKS(TARGET) ((TARGET) == APE_TARGET_ORI_CAL_LARM_UARM ? 5 : 4)
-#endif
+// Warps per CTA and resident CTAs per SM -> registers per thread.  The row math wants 96 registers (O = 12) / 128 (O = 14, 20) to run without
+// spills (measured, 32 768 estimates x 100 rows, four-warp CTAs: O = 12 at 80 / 96 / 128 registers 0.066 / 0.053 / 0.058 ms; O = 14 at
+// 96 / 128: 0.067 / 0.0666 ms, at 160: 0.071).  ONE warp per CTA (two estimates): 0.0524 ms against 0.0532 with four warps and 0.0576 with
+// eight (O = 14: 0.0651 / 0.0666 / 0.0699) - the finer the CTAs, the shorter the ragged end of the last wave, and a small launch (1024
+// estimates inside the pipeline) spreads over 512 CTAs instead of 128.
 #ifndef APE_FK_WARPS
-#define APE_FK_WARPS 4
+#define APE_FK_WARPS 1
+#endif
+#ifndef APE_FK_MIN_BLOCKS
+#define APE_FK_MIN_BLOCKS(TARGET) (((TARGET) == APE_TARGET_ORI_CAL_LARM_UARM ? 20 : 16) / APE_FK_WARPS)
 #endif
 constexpr int FK_WARPS_PER_CTA = APE_FK_WARPS;
 
