@@ -230,7 +230,7 @@ class BatchedEstimator:
             # 0.19 ms on the layer kernels, 32 streams 0.16 against 0.19, 64 streams 0.27 against 0.19 (tools/tcl_crossover.py).  Same operand rounding, accumulation order and Philox keys as the layer kernels: results are bit-identical
             # (tests/test_gpu_tcl.py), so it is simply what such an estimator runs (small_batch_kernel=False: the layer kernels).
             self.small_batch = (bool(small_batch_kernel) and self.lstm_variant == "tc" and not self.tc_split and self.tc_flags == 0
-                                and self.L <= 4 and self.H in (128, 256) and B * nF * self.n <= self.SMALL_BATCH_ROWS)
+                                and self.L <= 4 and self.H in (128, 256) and self.T <= 40 and B * nF * self.n <= self.SMALL_BATCH_ROWS)
             if self.small_batch:
                 self.tc_flags = 4
             # cross-call software pipeline (tensor-core path), two levels:
