@@ -96,7 +96,7 @@ constexpr uint32_t OUT_N = 32;                     // output product: 16 outputs
 constexpr uint32_t OUT_BYTES = KG * (OUT_N / 2) * 16;   // this CTA's tile of it (4 KB)
 constexpr uint32_t BAR_BLOCK_BYTES = 512;
 constexpr uint32_t SMEM = A_BYTES + 2 * A_BYTES + NMASK * MASK_BYTES + NP * SLOT_BYTES + ONES_BYTES + BAR_BLOCK_BYTES;
-constexpr uint32_t ACC_COLS = 256, HA_COL = 256, HB_COL = 384, H_COLS = H / 2, TMEM_COLS = 512;
+constexpr uint32_t HA_COL = 256 /* behind the two 128-column accumulator slots */, HB_COL = 384, H_COLS = H / 2, TMEM_COLS = 512;
 constexpr size_t CSTATE_FLOATS = (size_t)2 * H * ROWS;     // per CTA: [layer][k-group * 2 + half][row] float4
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 
